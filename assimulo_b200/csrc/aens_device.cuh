@@ -1,0 +1,747 @@
+/*
+ * aens_device.cuh -- device side of the ensemble integrator (sm_100a; also compiled by NVRTC for user models).
+ *
+ * One trajectory ("member") per thread, the complete Assimulo driver in the kernel:
+ *
+ *   Explicit_ODE._simulate segment loop          src/explicit_ode.pyx:137-274   -> aens_ens_kernel (phase machine)
+ *   Explicit_ODE.event_locator + f_event_locator src/explicit_ode.pyx:332-361,
+ *                                                src/ode_event_locator.c:17-149 -> aens_locate
+ *   report_solution grid interpolation           src/explicit_ode.pyx:308-318   -> aens_emit_grid
+ *   ExplicitEuler.integrate/_step/interpolate    src/solvers/euler.pyx:570-650  -> AensEuler
+ *   RungeKutta4._iter/_step                      src/solvers/runge_kutta.py:839-862 -> AensRK4
+ *   RungeKutta34._iter/_step/adjust_stepsize     src/solvers/runge_kutta.py:618-723 -> AensRK34
+ *   Dopri5.integrate/_solout + DOPCOR/HINIT/CONTD5 runge_kutta.py:78-188, thirdparty/hairer/dopri5.f:356-692
+ *                                                                                -> AensDopri5
+ *   (Radau5ODE lives in aens_radau5.cuh)
+ *
+ * Stage vectors are per-thread arrays with compile-time indices (fully unrolled) => registers.  Global memory
+ * is touched only when a member is fetched (y0, p, sw: SoA, coalesced when a warp fetches 32 consecutive
+ * members), when it finishes, for dense-output rows and for event-log entries.
+ *
+ * Two arithmetic builds of this same source (macro AENS_STRICT):
+ *   STRICT=1  compiled with --fmad=false; every expression keeps the reference's association order; pow/sqrt/div
+ *             are the fp64 library/IEEE versions.  Reproduces the CPU oracle step for step.
+ *   STRICT=0  FMA contraction allowed; the step-size controllers evaluate their fractional powers with the fp32
+ *             MUFU lg2/ex2 pair (they only steer h); the accept test and all state arithmetic stay fp64.
+ */
+#ifndef AENS_DEVICE_CUH
+#define AENS_DEVICE_CUH
+
+#include "aens_args.h"
+#include "aens_models.cuh"
+
+#ifndef AENS_STRICT
+#define AENS_STRICT 0
+#endif
+
+#define AENS_BLOCK 128
+
+/* return codes of Stepper::attempt (values of the reference's ID_PY_* where they exist, constants.pxi:54-58) */
+#define AENS_R_CONTINUE 0
+#define AENS_R_EVENT 2
+#define AENS_R_COMPLETE 3
+#define AENS_R_ERROR (-1)
+
+namespace aens {
+
+AENS_DEV double dabs(double x) { return fabs(x); }
+AENS_DEV double dmax(double a, double b) { return a >= b ? a : b; } /* Fortran MAX / radau_max / fmax on non-NaN */
+AENS_DEV double dmin(double a, double b) { return a <= b ? a : b; }
+
+#if !AENS_STRICT
+/* fp32 MUFU power for step-size heuristics only: x^e = ex2(e * lg2(x)).  x=0 -> 0, x=inf -> inf (e>0). */
+AENS_DEV float fpow(float x, float e) { return exp2f(e * __log2f(x)); }
+/* reciprocal of a strictly positive, normal fp64 number: MUFU.RCP64H seed + 2 Newton steps (~1 ulp) */
+AENS_DEV double rcp_pos(double b) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b));
+    double e = fma(-b, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-b, r, 1.0);
+    r = fma(r, e, r);
+    return r;
+}
+#endif
+
+/* ------------------------------------------------------------------------------------------------------- */
+/* Per-member state common to all solvers                                                                   */
+/* ------------------------------------------------------------------------------------------------------- */
+template <class M>
+struct Lane {
+    static constexpr int N = M::N, NP = (M::NP > 0 ? M::NP : 1), NG = (M::NG > 0 ? M::NG : 1),
+                         NSW = (M::NSW > 0 ? M::NSW : 1);
+    double t;
+    double y[N];
+    double p[NP];
+    double g_old[NG];
+    unsigned char sw[NSW];
+    int event_info[NG];
+    int st[AENS_NSTATS];
+    int gi;      /* next dense-output row */
+    int status;
+
+    AENS_DEV void rhs(double tt, const double *yy, double *yd) { M::rhs(tt, yy, sw, p, yd); }
+
+    AENS_DEV void load(const aens_args_t &a, long long idx) {
+        t = a.t[idx];
+#pragma unroll
+        for (int i = 0; i < M::N; ++i) y[i] = a.y[(long long)i * a.N + idx];
+#pragma unroll
+        for (int i = 0; i < M::NP; ++i) p[i] = a.p[(long long)i * a.N + idx];
+#pragma unroll
+        for (int i = 0; i < M::NSW; ++i) sw[i] = a.sw[(long long)i * a.N + idx];
+#pragma unroll
+        for (int i = 0; i < AENS_NSTATS; ++i) st[i] = 0;
+        gi = a.n_grid > 0 ? a.grid_idx[idx] : 0;
+        status = AENS_ST_COMPLETE;
+    }
+    AENS_DEV void store(const aens_args_t &a, long long idx) {
+        a.t[idx] = t;
+#pragma unroll
+        for (int i = 0; i < M::N; ++i) a.y[(long long)i * a.N + idx] = y[i];
+#pragma unroll
+        for (int i = 0; i < M::NSW; ++i) a.sw[(long long)i * a.N + idx] = sw[i];
+#pragma unroll
+        for (int i = 0; i < AENS_NSTATS; ++i) a.stats[(long long)i * a.N + idx] = st[i];
+        if (a.n_grid > 0) a.grid_idx[idx] = gi;
+        a.status[idx] = status;
+    }
+};
+
+/* set_problem_data() of every solver class (runge_kutta.py:78-97, euler.pyx:537-555, radau5.py:232-274):
+ * evaluate g at the segment start */
+template <class M>
+AENS_DEV void seg_init_events(Lane<M> &L) {
+    if (M::NG > 0) {
+        M::events(L.t, L.y, L.sw, L.p, L.g_old);
+        L.st[AENS_STAT_NSTATEFCNS] += 1;
+    }
+}
+
+/* src/ode_event_locator.c:17-149 wrapped as in src/explicit_ode.pyx:332-361.  `S::interp(x, out)` is the dense
+ * output of the step just taken.  On AENS_R_EVENT, t_high / y_high hold the event point. */
+template <class M, class S>
+AENS_DEV int aens_locate(S &s, Lane<M> &L, double t_low, double &t_high, double *y_high) {
+    constexpr int NG = M::NG > 0 ? M::NG : 1;
+    double g_low[NG], g_mid[NG], g_high[NG];
+#pragma unroll
+    for (int i = 0; i < M::NG; ++i) g_low[i] = L.g_old[i];
+    const double TOL = dmax(dabs(t_low), dabs(t_high)) * 1.e-13;
+    M::events(t_high, y_high, L.sw, L.p, g_high);
+    L.st[AENS_STAT_NSTATEFCNS] += 1;
+    bool ev = false;
+#pragma unroll
+    for (int i = 0; i < M::NG; ++i) ev = ev || ((g_low[i] > 0) != (g_high[i] > 0));
+    if (ev) {
+        int side = 0, sideprev = -1;
+        double alpha = 1.;
+        while (dabs(t_high - t_low) > TOL) {
+            if (side == sideprev) {
+                if (side == 2) alpha *= 2.; else alpha /= 2.;
+            } else {
+                alpha = 1.;
+            }
+            /* component with the largest |g_high/(g_low-g_high)| among the sign-changed ones (ties -> last) */
+            double maxfrac = 0., gh = g_high[0], gl = g_low[0];
+#pragma unroll
+            for (int i = 0; i < M::NG; ++i) {
+                if ((g_low[i] > 0) != (g_high[i] > 0)) {
+                    const double gfrac = dabs(g_high[i] / (g_low[i] - g_high[i]));
+                    if (gfrac >= maxfrac) { maxfrac = gfrac; gh = g_high[i]; gl = g_low[i]; }
+                }
+            }
+            double t_mid;
+            if (gh == 0 || gl == 0) t_mid = (t_low + t_high) / 2.;
+            else t_mid = t_high - (t_high - t_low) * gh / (gh - alpha * gl);
+            if (dabs(t_mid - t_low) < TOL / 2.) {
+                const double fracint = dabs(t_low - t_high) / TOL;
+                t_mid = t_low + (t_high - t_low) / (2. * dmin(fracint, 5.));
+            }
+            if (dabs(t_mid - t_high) < TOL / 2.) {
+                const double fracint = dabs(t_low - t_high) / TOL;
+                t_mid = t_high - (t_high - t_low) / (2. * dmin(fracint, 5.));
+            }
+            s.interp(t_mid, y_high);
+            M::events(t_mid, y_high, L.sw, L.p, g_mid);
+            L.st[AENS_STAT_NSTATEFCNS] += 1;
+            sideprev = side;
+            bool left = false;
+#pragma unroll
+            for (int i = 0; i < M::NG; ++i) left = left || ((g_low[i] > 0) != (g_mid[i] > 0));
+            if (left) {
+                t_high = t_mid;
+#pragma unroll
+                for (int i = 0; i < M::NG; ++i) g_high[i] = g_mid[i];
+                side = 1;
+            } else {
+                t_low = t_mid;
+#pragma unroll
+                for (int i = 0; i < M::NG; ++i) g_low[i] = g_mid[i];
+                side = 2;
+            }
+        }
+        s.interp(t_high, y_high);
+#pragma unroll
+        for (int i = 0; i < M::NG; ++i) {
+            L.event_info[i] = 0;
+            if ((g_low[i] > 0) != (g_high[i] > 0)) L.event_info[i] = (g_high[i] > 0) ? 1 : -1;
+        }
+        L.st[AENS_STAT_NSTATEEVENTS] += 1;
+    }
+#pragma unroll
+    for (int i = 0; i < M::NG; ++i) L.g_old[i] = g_high[i];
+    return ev ? AENS_R_EVENT : AENS_R_CONTINUE;
+}
+
+/* report_solution(): rows `while grid[k] <= t` from the interpolant of the last step (explicit_ode.pyx:308-318).
+ * Row layout [k][component][member]: lanes of a warp that emit the same row store 256 contiguous bytes. */
+template <class M, class S>
+AENS_DEV void aens_emit_grid(S &s, Lane<M> &L, const aens_args_t &a, long long idx, double t) {
+    while (L.gi < a.n_grid && __ldg(a.t_grid + L.gi) <= t) {
+        double out[M::N];
+        s.interp(__ldg(a.t_grid + L.gi), out);
+#pragma unroll
+        for (int i = 0; i < M::N; ++i) a.dense[((long long)L.gi * M::N + i) * a.N + idx] = out[i];
+        L.gi += 1;
+    }
+}
+
+/* After an accepted step [told, t] whose end state is in L.y: event location, then grid rows.
+ * Mirrors the order of Dopri5._solout / Radau5ODE._solout / the loops of RungeKutta34 and ExplicitEuler:
+ * locator first, then output up to the (possibly shortened) t. */
+template <class M, class S>
+AENS_DEV int aens_post_step(S &s, Lane<M> &L, const aens_args_t &a, long long idx, double told, double tnew) {
+    int flag = AENS_R_CONTINUE;
+    if (M::NG > 0) {
+        double te = tnew;
+        double ye[M::N];
+#pragma unroll
+        for (int i = 0; i < M::N; ++i) ye[i] = L.y[i];
+        flag = aens_locate<M, S>(s, L, told, te, ye);
+        if (flag == AENS_R_EVENT) {
+            tnew = te;
+#pragma unroll
+            for (int i = 0; i < M::N; ++i) L.y[i] = ye[i];
+        }
+    }
+    if (S::HAS_DENSE) aens_emit_grid<M, S>(s, L, a, idx, tnew);
+    L.t = tnew;
+    return flag;
+}
+
+/* ------------------------------------------------------------------------------------------------------- */
+/* ExplicitEuler, src/solvers/euler.pyx:570-650                                                              */
+/* ------------------------------------------------------------------------------------------------------- */
+template <class M, bool DENSE>
+struct Euler {
+    static constexpr bool HAS_DENSE = DENSE;
+    static constexpr int N = M::N;
+    Lane<M> L;
+    double h, inith;          /* inith = ExplicitEuler._inith: remainder of a grid step cut by an event */
+    double yold[DENSE ? N : 1], told, hstep;
+    bool pending;
+
+    AENS_DEV void load_aux(const aens_args_t &a, long long idx) { inith = a.aux[idx]; }
+    AENS_DEV void store_aux(const aens_args_t &a, long long idx) { a.aux[idx] = inith; }
+
+    AENS_DEV void interp(double x, double *out) { /* euler.pyx:649-650 */
+        if (DENSE) {
+#pragma unroll
+            for (int i = 0; i < N; ++i) out[i] = yold[i] + (x - told) / hstep * (L.y[i] - yold[i]);
+        }
+    }
+    AENS_DEV void seg_init(const aens_args_t &a, long long) {
+        h = dmin(a.o.h, dabs(a.tf - L.t));
+        seg_init_events(L);
+        pending = (inith != 0);
+    }
+    AENS_DEV void step(double hs) { /* euler.pyx:636-647 */
+        double f[N];
+        L.rhs(L.t, L.y, f);
+        L.st[AENS_STAT_NFCNS] += 1;
+        L.st[AENS_STAT_NSTEPS] += 1;
+        L.st[AENS_STAT_NSTEPSTOTAL] += 1;
+        told = L.t;
+        hstep = hs;
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            if (DENSE) yold[i] = L.y[i];
+            L.y[i] = L.y[i] + hs * f[i];
+        }
+    }
+    AENS_DEV int attempt(const aens_args_t &a, long long idx) {
+        if (pending) { /* euler.pyx:583-600 */
+            const double hs = inith;
+            step(hs);
+            const double tn = told + hs;
+            const int flag = aens_post_step<M, Euler>(*this, L, a, idx, tn - hs, tn);
+            pending = false;
+            if (flag == AENS_R_EVENT) inith = inith - (L.t - told);
+            else inith = 0;
+            h = dmin(h, dabs(a.tf - L.t));
+            if (flag == AENS_R_EVENT && inith == 0) { /* euler.pyx:629-632 */
+                inith = h - (L.t - told);
+                if (!(dabs(inith) > 1e-15)) inith = 0.0;
+            }
+            return flag;
+        }
+        const bool inner = (L.t + h < a.tf);
+        const double hs = h;
+        step(hs);
+        const double tn = told + hs;
+        int flag = aens_post_step<M, Euler>(*this, L, a, idx, tn - hs, tn);
+        if (inner) h = dmin(h, dabs(a.tf - L.t));
+        if (flag == AENS_R_EVENT) {
+            if (inith == 0) { /* euler.pyx:629-632 */
+                inith = h - (L.t - told);
+                if (!(dabs(inith) > 1e-15)) inith = 0.0;
+            }
+            return AENS_R_EVENT;
+        }
+        return inner ? AENS_R_CONTINUE : AENS_R_COMPLETE;
+    }
+};
+
+/* ------------------------------------------------------------------------------------------------------- */
+/* RungeKutta4, src/solvers/runge_kutta.py:839-862 (no events, no dense output in the reference)            */
+/* ------------------------------------------------------------------------------------------------------- */
+template <class M, bool DENSE>
+struct RK4 {
+    static constexpr bool HAS_DENSE = false;
+    static constexpr int N = M::N;
+    Lane<M> L;
+    double h;
+    AENS_DEV void load_aux(const aens_args_t &, long long) {}
+    AENS_DEV void store_aux(const aens_args_t &, long long) {}
+    AENS_DEV void interp(double, double *) {}
+    AENS_DEV void seg_init(const aens_args_t &a, long long) { h = dmin(a.o.h, dabs(a.tf - L.t)); }
+    AENS_DEV int attempt(const aens_args_t &a, long long) {
+        const bool inner = (L.t + h < a.tf);
+        double Y1[N], Y2[N], Y3[N], Y4[N], arg[N];
+        const double t = L.t;
+        L.rhs(t, L.y, Y1);
+#pragma unroll
+        for (int i = 0; i < N; ++i) arg[i] = L.y[i] + h * Y1[i] / 2.;
+        L.rhs(t + h / 2., arg, Y2);
+#pragma unroll
+        for (int i = 0; i < N; ++i) arg[i] = L.y[i] + h * Y2[i] / 2.;
+        L.rhs(t + h / 2., arg, Y3);
+#pragma unroll
+        for (int i = 0; i < N; ++i) arg[i] = L.y[i] + h * Y3[i];
+        L.rhs(t + h, arg, Y4);
+        const double h6 = h / 6.;
+#pragma unroll
+        for (int i = 0; i < N; ++i) L.y[i] = L.y[i] + h6 * (Y1[i] + 2. * Y2[i] + 2. * Y3[i] + Y4[i]);
+        L.t = t + h;
+        L.st[AENS_STAT_NFCNS] += 4;
+        L.st[AENS_STAT_NSTEPS] += 1;
+        L.st[AENS_STAT_NSTEPSTOTAL] += 1;
+        if (inner) { h = dmin(h, dabs(a.tf - L.t)); return AENS_R_CONTINUE; }
+        return AENS_R_COMPLETE;
+    }
+};
+
+/* ------------------------------------------------------------------------------------------------------- */
+/* RungeKutta34, src/solvers/runge_kutta.py:618-723                                                          */
+/* ------------------------------------------------------------------------------------------------------- */
+template <class M, bool DENSE>
+struct RK34 {
+    static constexpr bool HAS_DENSE = DENSE;
+    static constexpr int N = M::N;
+    Lane<M> L;
+    double h, Y1[N];
+    double yold[DENSE ? N : 1], flow[DENSE ? N : 1], told, tnext, hstep;
+    int it;
+
+    AENS_DEV void load_aux(const aens_args_t &, long long) {}
+    AENS_DEV void store_aux(const aens_args_t &, long long) {}
+    AENS_DEV void interp(double time, double *out) { /* Hermite, runge_kutta.py:715-720; f_high = Y1 */
+        if (DENSE) {
+            const double th = (time - told) / (tnext - told);
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+                const double y = yold[i], yn = L.y[i];
+                out[i] = (1 - th) * y + th * yn + th * (th - 1) *
+                         ((1 - 2 * th) * (yn - y) + (th - 1) * hstep * flow[i] + th * hstep * Y1[i]);
+            }
+        }
+    }
+    AENS_DEV void seg_init(const aens_args_t &a, long long) {
+        seg_init_events(L);
+        h = dmin(a.o.inith, dabs(a.tf - L.t));
+        L.rhs(L.t, L.y, Y1);
+        it = 0;
+    }
+    AENS_DEV int attempt(const aens_args_t &a, long long idx) {
+        const bool inner = (L.t + h < a.tf);
+        if (it >= a.o.maxsteps) { /* for-else: 'Final time not reached within maximum number of steps' */
+            L.status = AENS_ST_MAXSTEPS;
+            return AENS_R_ERROR;
+        }
+        double Y2[N], Y3[N], Z3[N], Y4[N], arg[N], sc[N];
+        const double t = L.t;
+        L.st[AENS_STAT_NFCNS] += 5;
+#pragma unroll
+        for (int i = 0; i < N; ++i) sc[i] = dabs(L.y[i]) * a.o.rtol + a.o.atol[i];
+#pragma unroll
+        for (int i = 0; i < N; ++i) arg[i] = L.y[i] + h * Y1[i] / 2.;
+        L.rhs(t + h / 2., arg, Y2);
+#pragma unroll
+        for (int i = 0; i < N; ++i) arg[i] = L.y[i] + h * Y2[i] / 2.;
+        L.rhs(t + h / 2., arg, Y3);
+#pragma unroll
+        for (int i = 0; i < N; ++i) arg[i] = L.y[i] - h * Y1[i] + 2.0 * h * Y2[i];
+        L.rhs(t + h, arg, Z3);
+#pragma unroll
+        for (int i = 0; i < N; ++i) arg[i] = L.y[i] + h * Y3[i];
+        L.rhs(t + h, arg, Y4);
+        const double h6 = h / 6.0;
+        double err2 = 0.;
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+#if AENS_STRICT
+            const double e = h6 * (2.0 * Y2[i] + Z3[i] - 2.0 * Y3[i] - Y4[i]) / sc[i];
+            err2 = fma(e, e, err2); /* numpy x.dot(x) = OpenBLAS ddot accumulates fused (oracle/ens_oracle.c) */
+#else
+            const double e = h6 * (2.0 * Y2[i] + Z3[i] - 2.0 * Y3[i] - Y4[i]) * rcp_pos(sc[i]);
+            err2 = fma(e, e, err2);
+#endif
+        }
+        const double tn = t + h;
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            if (DENSE) { yold[i] = L.y[i]; flow[i] = Y1[i]; }
+            L.y[i] = L.y[i] + h6 * (Y1[i] + 2.0 * Y2[i] + 2.0 * Y3[i] + Y4[i]);
+        }
+        L.rhs(tn, L.y, Y1);
+        told = t; tnext = tn; hstep = h;
+        L.st[AENS_STAT_NSTEPS] += 1;
+        L.st[AENS_STAT_NSTEPSTOTAL] += 1;
+        const int flag = aens_post_step<M, RK34>(*this, L, a, idx, tn - h, tn);
+        if (inner) {
+            /* adjust_stepsize, runge_kutta.py:682-692 */
+            double fac;
+#if AENS_STRICT
+            const double error = sqrt(err2);
+            if (error == 0.0) fac = 2.0;
+            else fac = dmin(pow(1.0 / error, 1.0 / 4.0), 2.);
+#else
+            /* (1/err)^(1/4) = err2^(-1/8); err2 == 0 -> +inf -> clipped to 2 */
+            fac = (double)fminf(fpow((float)err2, -0.125f), 2.0f);
+            if (!(err2 > 0.0)) fac = 2.0;
+#endif
+            h = h * fac;
+            h = dmin(h, dabs(a.tf - L.t));
+            it += 1;
+        }
+        if (flag == AENS_R_EVENT) return AENS_R_EVENT;
+        return inner ? AENS_R_CONTINUE : AENS_R_COMPLETE;
+    }
+};
+
+/* ------------------------------------------------------------------------------------------------------- */
+/* Dopri5: DOPCOR dopri5.f:356-556, HINIT :558-619, CONTD5 :621-644, CDOPRI :646-692                         */
+/* ------------------------------------------------------------------------------------------------------- */
+namespace dp {
+constexpr double c2 = 0.2, c3 = 0.3, c4 = 0.8, c5 = 8.0 / 9.0;
+constexpr double a21 = 0.2, a31 = 3.0 / 40.0, a32 = 9.0 / 40.0, a41 = 44.0 / 45.0, a42 = -56.0 / 15.0,
+                 a43 = 32.0 / 9.0, a51 = 19372.0 / 6561.0, a52 = -25360.0 / 2187.0, a53 = 64448.0 / 6561.0,
+                 a54 = -212.0 / 729.0, a61 = 9017.0 / 3168.0, a62 = -355.0 / 33.0, a63 = 46732.0 / 5247.0,
+                 a64 = 49.0 / 176.0, a65 = -5103.0 / 18656.0, a71 = 35.0 / 384.0, a73 = 500.0 / 1113.0,
+                 a74 = 125.0 / 192.0, a75 = -2187.0 / 6784.0, a76 = 11.0 / 84.0;
+constexpr double e1 = 71.0 / 57600.0, e3 = -71.0 / 16695.0, e4 = 71.0 / 1920.0, e5 = -17253.0 / 339200.0,
+                 e6 = 22.0 / 525.0, e7 = -1.0 / 40.0;
+constexpr double d1 = -12715105075.0 / 11282082432.0, d3 = 87487479700.0 / 32700410799.0,
+                 d4 = -10690763975.0 / 1880347072.0, d5 = 701980252875.0 / 199316789632.0,
+                 d6 = -1453857185.0 / 822651844.0, d7 = 69997945.0 / 29380423.0;
+constexpr double uround = 2.3e-16; /* dopri5.f:253-254 */
+}  // namespace dp
+
+template <class M, bool DENSE>
+struct Dopri5 {
+    static constexpr bool HAS_DENSE = DENSE;
+    static constexpr int N = M::N;
+    Lane<M> L;
+    double k1[N];
+    double h, hmax;
+    double facold;             /* STRICT: FACOLD; FAST: FACOLD**2 */
+    double cont[DENSE ? 5 * N : 1], told, hstep;
+    int nstep, naccpt;         /* per dopri5() call, i.e. per segment */
+    bool last, reject;
+
+    AENS_DEV void load_aux(const aens_args_t &, long long) {}
+    AENS_DEV void store_aux(const aens_args_t &, long long) {}
+
+    AENS_DEV void interp(double x, double *out) { /* CONTD5 */
+        if (DENSE) {
+            const double th = (x - told) / hstep, th1 = 1.0 - th;
+#pragma unroll
+            for (int i = 0; i < N; ++i)
+                out[i] = cont[i] + th * (cont[N + i] + th1 * (cont[2 * N + i] + th * (cont[3 * N + i] + th1 * cont[4 * N + i])));
+        }
+    }
+
+    AENS_DEV double hinit(const aens_args_t &a) { /* HINIT with IORD=5, ITOL=1, POSNEG=+1 */
+        double dnf = 0.0, dny = 0.0;
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            const double sk = a.o.atol[i] + a.o.rtol * dabs(L.y[i]);
+            const double q1 = k1[i] / sk, q2 = L.y[i] / sk;
+            dnf = dnf + q1 * q1;
+            dny = dny + q2 * q2;
+        }
+        double hh;
+        if (dnf <= 1.0e-10 || dny <= 1.0e-10) hh = 1.0e-6;
+        else hh = sqrt(dny / dnf) * 0.01;
+        hh = dmin(hh, hmax);
+        double y1[N], f1[N];
+#pragma unroll
+        for (int i = 0; i < N; ++i) y1[i] = L.y[i] + hh * k1[i];
+        L.rhs(L.t + hh, y1, f1);
+        double der2 = 0.0;
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            const double sk = a.o.atol[i] + a.o.rtol * dabs(L.y[i]);
+            const double q = (f1[i] - k1[i]) / sk;
+            der2 = der2 + q * q;
+        }
+        der2 = sqrt(der2) / hh;
+        const double der12 = dmax(dabs(der2), sqrt(dnf));
+        double h1;
+        if (der12 <= 1.0e-15) h1 = dmax(1.0e-6, dabs(hh) * 1.0e-3);
+        else h1 = pow(0.01 / der12, 1.0 / 5);
+        return dmin(dmin(100 * dabs(hh), h1), hmax);
+    }
+
+    AENS_DEV void seg_init(const aens_args_t &a, long long idx) {
+        seg_init_events(L);
+        hmax = dabs((a.o.maxh == 0.0) ? (a.tf - L.t) : a.o.maxh); /* dopri5.f:301-305, :392 */
+#if AENS_STRICT
+        facold = 1.0e-4;
+#else
+        facold = 1.0e-8;
+#endif
+        last = false;
+        reject = false;
+        nstep = 0;
+        naccpt = 0;
+        L.rhs(L.t, L.y, k1);
+        h = a.o.inith;
+        if (h == 0.0) h = hinit(a);
+        L.st[AENS_STAT_NFCNS] += 2;
+        /* first SOLOUT call (XOLD = X, dopri5.f:399-404): Assimulo runs the locator on a zero-length interval --
+         * one more g evaluation at the very same point, never an event -- and reports grid rows <= t */
+        if (M::NG > 0) L.st[AENS_STAT_NSTATEFCNS] += 1;
+        if (DENSE) {
+            while (L.gi < a.n_grid && __ldg(a.t_grid + L.gi) <= L.t) {
+#pragma unroll
+                for (int i = 0; i < N; ++i) a.dense[((long long)L.gi * N + i) * a.N + idx] = L.y[i];
+                L.gi += 1;
+            }
+        }
+    }
+
+    AENS_DEV int attempt(const aens_args_t &a, long long idx) {
+        using namespace dp;
+        if (nstep > a.o.maxsteps) { L.status = AENS_ST_MAXSTEPS; return AENS_R_ERROR; }
+        if (0.1 * dabs(h) <= dabs(L.t) * uround) { L.status = AENS_ST_STEP_TOO_SMALL; return AENS_R_ERROR; }
+        const double x = L.t;
+        if ((x + 1.01 * h - a.tf) > 0.0) { h = a.tf - x; last = true; }
+        nstep += 1;
+        L.st[AENS_STAT_NSTEPSTOTAL] += 1;
+        double k2[N], k3[N], k4[N], k5[N], k6[N], y1[N];
+#pragma unroll
+        for (int i = 0; i < N; ++i) y1[i] = L.y[i] + h * a21 * k1[i];
+        L.rhs(x + c2 * h, y1, k2);
+#pragma unroll
+        for (int i = 0; i < N; ++i) y1[i] = L.y[i] + h * (a31 * k1[i] + a32 * k2[i]);
+        L.rhs(x + c3 * h, y1, k3);
+#pragma unroll
+        for (int i = 0; i < N; ++i) y1[i] = L.y[i] + h * (a41 * k1[i] + a42 * k2[i] + a43 * k3[i]);
+        L.rhs(x + c4 * h, y1, k4);
+#pragma unroll
+        for (int i = 0; i < N; ++i) y1[i] = L.y[i] + h * (a51 * k1[i] + a52 * k2[i] + a53 * k3[i] + a54 * k4[i]);
+        L.rhs(x + c5 * h, y1, k5);
+#pragma unroll
+        for (int i = 0; i < N; ++i)
+            y1[i] = L.y[i] + h * (a61 * k1[i] + a62 * k2[i] + a63 * k3[i] + a64 * k4[i] + a65 * k5[i]);
+        const double xph = x + h;
+        L.rhs(xph, y1, k6);
+#pragma unroll
+        for (int i = 0; i < N; ++i)
+            y1[i] = L.y[i] + h * (a71 * k1[i] + a73 * k3[i] + a74 * k4[i] + a75 * k5[i] + a76 * k6[i]);
+        L.rhs(xph, y1, k2); /* FSAL stage kept in K2 */
+        L.st[AENS_STAT_NFCNS] += 6;
+        double c4v[DENSE ? N : 1];
+        double err2 = 0.0;
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            if (DENSE) c4v[i] = h * (d1 * k1[i] + d3 * k3[i] + d4 * k4[i] + d5 * k5[i] + d6 * k6[i] + d7 * k2[i]);
+            const double ei = (e1 * k1[i] + e3 * k3[i] + e4 * k4[i] + e5 * k5[i] + e6 * k6[i] + e7 * k2[i]) * h;
+            const double sk = a.o.atol[i] + a.o.rtol * dmax(dabs(L.y[i]), dabs(y1[i]));
+#if AENS_STRICT
+            const double q = ei / sk;
+            err2 = err2 + q * q;
+#else
+            const double q = ei * rcp_pos(sk);
+            err2 = fma(q, q, err2);
+#endif
+        }
+        double hnew;
+        bool accept;
+#if AENS_STRICT
+        const double err = sqrt(err2 / N);
+        const double expo1 = 0.2 - a.o.beta * 0.75;
+        const double facc1 = 1.0 / a.o.fac1, facc2 = 1.0 / a.o.fac2;
+        const double fac11 = pow(err, expo1);
+        double fac = fac11 / pow(facold, a.o.beta);
+        fac = dmax(facc2, dmin(facc1, fac / a.o.safe));
+        hnew = h / fac;
+        accept = (err <= 1.0);
+        if (accept) facold = dmax(err, 1.0e-4);
+        else hnew = h / dmin(facc1, fac11 / a.o.safe);
+#else
+        {
+            /* controller in fp32 on the squared norm: err^e = (err2)^(e/2) */
+            const double e2 = err2 * (1.0 / N);
+            const float expo1h = 0.5f * (float)(0.2 - a.o.beta * 0.75), betah = 0.5f * (float)a.o.beta;
+            const float facc1 = 1.0f / (float)a.o.fac1, facc2 = 1.0f / (float)a.o.fac2;
+            const float rsafe = 1.0f / (float)a.o.safe;
+            const float fac11 = fpow((float)e2, expo1h);
+            accept = (e2 <= 1.0);
+            float fac;
+            if (accept) {
+                fac = __fdividef(fac11, fpow((float)facold, betah));
+                fac = fmaxf(facc2, fminf(facc1, fac * rsafe));
+                facold = dmax(e2, 1.0e-8);
+            } else {
+                fac = fminf(facc1, fac11 * rsafe);
+            }
+            hnew = h * (double)__fdividef(1.0f, fac);
+        }
+#endif
+        if (accept) {
+            naccpt += 1;
+            L.st[AENS_STAT_NSTEPS] += 1;
+            /* (stiffness detection dopri5.f:474-494 only prints under Assimulo's IPRINT: omitted) */
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+                if (DENSE) {
+                    const double ydiff = y1[i] - L.y[i];
+                    const double bspl = h * k1[i] - ydiff;
+                    cont[i] = L.y[i];
+                    cont[N + i] = ydiff;
+                    cont[2 * N + i] = bspl;
+                    cont[3 * N + i] = -h * k2[i] + ydiff - bspl;
+                    cont[4 * N + i] = c4v[i];
+                }
+                k1[i] = k2[i];
+                L.y[i] = y1[i];
+            }
+            told = x;
+            hstep = h;
+            const int flag = aens_post_step<M, Dopri5>(*this, L, a, idx, x, xph);
+            if (flag == AENS_R_EVENT) return AENS_R_EVENT;
+            if (last) return AENS_R_COMPLETE;
+            if (dabs(hnew) > hmax) hnew = hmax;
+            if (reject) hnew = dmin(dabs(hnew), dabs(h));
+            reject = false;
+        } else {
+            reject = true;
+            if (naccpt >= 1) L.st[AENS_STAT_NERRFAILS] += 1;
+            last = false;
+        }
+        h = hnew;
+        return AENS_R_CONTINUE;
+    }
+};
+
+}  // namespace aens
+
+/* ------------------------------------------------------------------------------------------------------- */
+/* The ensemble kernel: persistent warps pull members from an atomic queue; every lane runs the phase        */
+/* machine  FETCH -> SEGINIT -> STEP* -> (EVENT -> handle_event -> SEGINIT | DONE -> STORE -> FETCH).          */
+/* ------------------------------------------------------------------------------------------------------- */
+template <class S, class M>
+__device__ __forceinline__ void aens_run(const aens_args_t &a) {
+    enum { PH_IDLE = 0, PH_SEGINIT = 1, PH_STEP = 2 };
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const double eps = 2.220446049250313e-16 * 100; /* explicit_ode.pyx:184 */
+    S s;
+    long long idx = -1;
+    int phase = PH_IDLE;
+    bool drained = false; /* warp-uniform: the queue has no more members */
+    for (;;) {
+        const unsigned idle_mask = __ballot_sync(FULL, phase == PH_IDLE);
+        if (idle_mask == FULL && drained) break;
+        if (!drained && (idle_mask == FULL || __popc(idle_mask) >= a.refill_threshold)) {
+            const int nidle = __popc(idle_mask);
+            const int leader = __ffs(idle_mask) - 1;
+            unsigned long long base = 0;
+            if (lane == leader) base = atomicAdd(a.queue, (unsigned long long)nidle);
+            base = __shfl_sync(FULL, base, leader);
+            if (phase == PH_IDLE) {
+                const long long q = (long long)base + __popc(idle_mask & ((1u << lane) - 1u));
+                if (q < a.N) {
+                    idx = a.order ? (long long)a.order[q] : q;
+                    s.L.load(a, idx);
+                    s.load_aux(a, idx);
+                    /* driver loop test, explicit_ode.pyx:209 */
+                    if (s.L.t + eps * aens::dmax(aens::dabs(s.L.t), aens::dabs(a.tf)) < a.tf) phase = PH_SEGINIT;
+                    else { s.L.store(a, idx); s.store_aux(a, idx); }
+                }
+            }
+            if ((long long)base + nidle >= a.N) drained = true;
+        }
+        if (phase == PH_SEGINIT) {
+            s.seg_init(a, idx);
+            phase = PH_STEP;
+        }
+        if (phase == PH_STEP) {
+            const int r = s.attempt(a, idx);
+            if (r != AENS_R_CONTINUE) {
+                bool done = true;
+                if (r == AENS_R_EVENT) {
+                    /* explicit_ode.pyx:233-264: log, handle_event, restart the solver (initialize=True) */
+                    const int ne = s.L.st[AENS_STAT_NSTATEEVENTS] - 1;
+                    if (a.ev_slots > 0) {
+                        int mask = 0;
+#pragma unroll
+                        for (int i = 0; i < M::NG; ++i)
+                            if (s.L.event_info[i] != 0)
+                                mask |= (1 << (2 * i)) | ((s.L.event_info[i] > 0 ? 1 : 0) << (2 * i + 1));
+                        const long long slot = (long long)(ne % a.ev_slots) * a.N + idx;
+                        a.ev_t[slot] = s.L.t;
+                        a.ev_info[slot] = mask;
+                    }
+                    const int term = M::handle_event(s.L.t, s.L.y, s.L.sw, s.L.event_info, s.L.p);
+                    if (term) s.L.status = AENS_ST_TERMINATED;
+                    else if (s.L.t != a.tf &&
+                             s.L.t + eps * aens::dmax(aens::dabs(s.L.t), aens::dabs(a.tf)) < a.tf) {
+                        phase = PH_SEGINIT;
+                        done = false;
+                    }
+                } else if (r == AENS_R_COMPLETE) {
+                    if (s.L.t != a.tf && s.L.t + eps * aens::dmax(aens::dabs(s.L.t), aens::dabs(a.tf)) < a.tf) {
+                        phase = PH_SEGINIT; /* integrate() returned short of tfinal: the driver calls it again */
+                        done = false;
+                    }
+                }
+                if (done) {
+                    s.L.store(a, idx);
+                    s.store_aux(a, idx);
+                    phase = PH_IDLE;
+                    idx = -1;
+                }
+            }
+        }
+    }
+}
+
+#define AENS_DEFINE_KERNEL(NAME, STEPPER, MODEL, DENSE, MINBLOCKS)                                   \
+    extern "C" __global__ void __launch_bounds__(AENS_BLOCK, MINBLOCKS) NAME(const aens_args_t a) {  \
+        aens_run<aens::STEPPER<MODEL, DENSE>, MODEL>(a);                                             \
+    }
+
+#endif /* AENS_DEVICE_CUH */

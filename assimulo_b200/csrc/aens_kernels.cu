@@ -1,0 +1,42 @@
+/*
+ * One translation unit per (built-in model, arithmetic mode): compiled as
+ *   nvcc -DAENS_KMODEL=AensVdp -DAENS_KNAME=vdp -DAENS_STRICT=1 --fmad=false ...   -> strict kernels
+ *   nvcc -DAENS_KMODEL=AensVdp -DAENS_KNAME=vdp -DAENS_STRICT=0 ...                -> fast kernels
+ * and exporting one lookup function  aens_kernels_<name>_<s|f>(solver, dense) -> kernel entry point.
+ */
+#include "aens_device.cuh"
+#include "aens_radau5.cuh"
+
+#define AENS_CAT_(a, b) a##b
+#define AENS_CAT(a, b) AENS_CAT_(a, b)
+#if AENS_STRICT
+#define AENS_SUF _s
+#else
+#define AENS_SUF _f
+#endif
+#define KN(base) AENS_CAT(AENS_CAT(AENS_CAT(base, AENS_KNAME), _), AENS_CAT(x, AENS_SUF))
+
+typedef AENS_KMODEL KM;
+constexpr bool kEvents = (KM::NG > 0);
+
+AENS_DEFINE_KERNEL(KN(aens_euler_d1_), Euler, KM, true, 1)
+AENS_DEFINE_KERNEL(KN(aens_rk4_d0_), RK4, KM, false, 1)
+AENS_DEFINE_KERNEL(KN(aens_rk34_d1_), RK34, KM, true, 1)
+AENS_DEFINE_KERNEL(KN(aens_dopri5_d1_), Dopri5, KM, true, 1)
+AENS_DEFINE_KERNEL(KN(aens_radau5_d1_), Radau5, KM, true, 1)
+/* models without events additionally get dense-free variants (no interpolation data kept in registers) */
+AENS_DEFINE_KERNEL(KN(aens_euler_d0_), Euler, KM, kEvents, 1)
+AENS_DEFINE_KERNEL(KN(aens_rk34_d0_), RK34, KM, kEvents, 1)
+AENS_DEFINE_KERNEL(KN(aens_dopri5_d0_), Dopri5, KM, kEvents, 1)
+AENS_DEFINE_KERNEL(KN(aens_radau5_d0_), Radau5, KM, kEvents, 1)
+
+extern "C" const void *AENS_CAT(AENS_CAT(aens_kernels_, AENS_KNAME), AENS_SUF)(int solver, int dense) {
+    switch (solver) {
+    case AENS_SOLVER_EULER: return dense ? (const void *)KN(aens_euler_d1_) : (const void *)KN(aens_euler_d0_);
+    case AENS_SOLVER_RK4: return (const void *)KN(aens_rk4_d0_);
+    case AENS_SOLVER_RK34: return dense ? (const void *)KN(aens_rk34_d1_) : (const void *)KN(aens_rk34_d0_);
+    case AENS_SOLVER_DOPRI5: return dense ? (const void *)KN(aens_dopri5_d1_) : (const void *)KN(aens_dopri5_d0_);
+    case AENS_SOLVER_RADAU5: return dense ? (const void *)KN(aens_radau5_d1_) : (const void *)KN(aens_radau5_d0_);
+    }
+    return nullptr;
+}

@@ -1,0 +1,197 @@
+/*
+ * Built-in model library: right-hand sides, Jacobians, event functions and handle_event as CUDA device
+ * functions (a Python callable cannot run on the device; this replaces Explicit_Problem.rhs/jac/state_events/
+ * handle_event, src/problem.pyx:403-488).  Each struct is the device twin of a model the reference ships:
+ *
+ *   Vdp        examples/radau5ode_vanderpol.py:42-48       (mu as parameter p[0])
+ *   Ball       examples/lsodar_bouncing_ball.py:28-75      p = [g, restitution]
+ *   Robertson  examples/radau5ode_with_jac_sparse.py:46-62 p = [k1, k2, k3]
+ *   Gyro       examples/cvode_gyro.py:39-57 (12 states)    p = [I1, I2, I3]
+ *   Linear     y' = p0*y + p1 (tests/solvers/test_rungekutta.py:40-47, examples/dopri5_basic.py)
+ *   LinearEv   + g = y - p2, handle_event: sw[0] <- False  (tests/test_solvers.py:27-57)
+ *   Extended   tests/conftest.py:26-114 Extended_Problem (event iteration inside handle_event)
+ *
+ * Interface of a model M (all static, all __device__):
+ *   constexpr int N, NP, NG, NSW; constexpr bool HAS_JAC;
+ *   void rhs(double t, const double* y, const unsigned char* sw, const double* p, double* yd);
+ *   void jac(t, y, sw, p, double* J)            column-major J[i + j*N] = d f_i / d y_j
+ *   void events(t, y, sw, p, double* g);
+ *   int  handle_event(double t, double* y, unsigned char* sw, const int* event_info, const double* p);
+ * The operation order inside each rhs is the order of the Python model, so that the STRICT build reproduces the
+ * reference's floating-point results bit for bit.
+ */
+#ifndef AENS_MODELS_CUH
+#define AENS_MODELS_CUH
+
+#define AENS_DEV __device__ __forceinline__
+
+struct AensVdp {
+    static constexpr int N = 2, NP = 1, NG = 0, NSW = 0;
+    static constexpr bool HAS_JAC = true;
+    static AENS_DEV void rhs(double, const double *y, const unsigned char *, const double *p, double *yd) {
+        yd[0] = y[1];
+        yd[1] = p[0] * ((1. - y[0] * y[0]) * y[1] - y[0]);
+    }
+    static AENS_DEV void jac(double, const double *y, const unsigned char *, const double *p, double *J) {
+        J[0] = 0.;
+        J[1] = p[0] * (-2. * y[0] * y[1] - 1.);
+        J[2] = 1.;
+        J[3] = p[0] * (1. - y[0] * y[0]);
+    }
+    static AENS_DEV void events(double, const double *, const unsigned char *, const double *, double *) {}
+    static AENS_DEV int handle_event(double, double *, unsigned char *, const int *, const double *) { return 0; }
+};
+
+struct AensBall {
+    static constexpr int N = 2, NP = 2, NG = 2, NSW = 2;
+    static constexpr bool HAS_JAC = false;
+    static AENS_DEV void rhs(double, const double *y, const unsigned char *, const double *p, double *yd) {
+        yd[0] = y[1];
+        yd[1] = p[0];
+    }
+    static AENS_DEV void jac(double, const double *, const unsigned char *, const double *, double *J) {
+        J[0] = 0.; J[1] = 0.; J[2] = 1.; J[3] = 0.;
+    }
+    static AENS_DEV void events(double, const double *y, const unsigned char *sw, const double *, double *g) {
+        g[0] = sw[0] ? y[0] : 5.;
+        g[1] = sw[1] ? y[1] : 5.;
+    }
+    static AENS_DEV int handle_event(double, double *y, unsigned char *sw, const int *info, const double *p) {
+        if (info[0] != 0) { sw[0] = 0; sw[1] = 1; y[1] = -p[1] * y[1]; }
+        else              { sw[0] = 1; sw[1] = 0; }
+        return 0;
+    }
+};
+
+struct AensRobertson {
+    static constexpr int N = 3, NP = 3, NG = 0, NSW = 0;
+    static constexpr bool HAS_JAC = true;
+    static AENS_DEV void rhs(double, const double *y, const unsigned char *, const double *p, double *yd) {
+        double yd0 = -p[0] * y[0] + p[1] * y[1] * y[2];
+        double yd2 = p[2] * y[1] * y[1];
+        yd[0] = yd0;
+        yd[1] = -yd0 - yd2;
+        yd[2] = yd2;
+    }
+    static AENS_DEV void jac(double, const double *y, const unsigned char *, const double *p, double *J) {
+        J[0] = -p[0];        J[1] = p[0];                                J[2] = 0.;
+        J[3] = p[1] * y[2];  J[4] = -p[1] * y[2] - 2. * p[2] * y[1];     J[5] = 2. * p[2] * y[1];
+        J[6] = p[1] * y[1];  J[7] = -p[1] * y[1];                        J[8] = 0.;
+    }
+    static AENS_DEV void events(double, const double *, const unsigned char *, const double *, double *) {}
+    static AENS_DEV int handle_event(double, double *, unsigned char *, const int *, const double *) { return 0; }
+};
+
+struct AensGyro {
+    static constexpr int N = 12, NP = 3, NG = 0, NSW = 0;
+    static constexpr bool HAS_JAC = false;
+    static AENS_DEV void rhs(double, const double *u, const unsigned char *, const double *p, double *ud) {
+        const double om0 = u[0] / p[0], om1 = u[1] / p[1], om2 = u[2] / p[2];
+        ud[0] = om2 * u[1] + (-om1) * u[2];
+        ud[1] = (-om2) * u[0] + om0 * u[2];
+        ud[2] = om1 * u[0] + (-om0) * u[1];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const double q0 = u[3 + c], q1 = u[6 + c], q2 = u[9 + c];
+            ud[3 + c] = om2 * q1 + (-om1) * q2;
+            ud[6 + c] = (-om2) * q0 + om0 * q2;
+            ud[9 + c] = om1 * q0 + (-om0) * q1;
+        }
+    }
+    static AENS_DEV void jac(double, const double *, const unsigned char *, const double *, double *) {}
+    static AENS_DEV void events(double, const double *, const unsigned char *, const double *, double *) {}
+    static AENS_DEV int handle_event(double, double *, unsigned char *, const int *, const double *) { return 0; }
+};
+
+struct AensLinear {
+    static constexpr int N = 1, NP = 3, NG = 0, NSW = 0;
+    static constexpr bool HAS_JAC = true;
+    static AENS_DEV void rhs(double, const double *y, const unsigned char *, const double *p, double *yd) {
+        yd[0] = p[0] * y[0] + p[1];
+    }
+    static AENS_DEV void jac(double, const double *, const unsigned char *, const double *p, double *J) { J[0] = p[0]; }
+    static AENS_DEV void events(double, const double *, const unsigned char *, const double *, double *) {}
+    static AENS_DEV int handle_event(double, double *, unsigned char *, const int *, const double *) { return 0; }
+};
+
+struct AensLinearEv {
+    static constexpr int N = 1, NP = 3, NG = 1, NSW = 1;
+    static constexpr bool HAS_JAC = true;
+    static AENS_DEV void rhs(double, const double *y, const unsigned char *, const double *p, double *yd) {
+        yd[0] = p[0] * y[0] + p[1];
+    }
+    static AENS_DEV void jac(double, const double *, const unsigned char *, const double *p, double *J) { J[0] = p[0]; }
+    static AENS_DEV void events(double, const double *y, const unsigned char *, const double *p, double *g) {
+        g[0] = y[0] - p[2];
+    }
+    static AENS_DEV int handle_event(double, double *, unsigned char *sw, const int *, const double *) {
+        sw[0] = 0;
+        return 0;
+    }
+};
+
+struct AensExtended {
+    static constexpr int N = 3, NP = 0, NG = 3, NSW = 3;
+    static constexpr bool HAS_JAC = false;
+    static AENS_DEV void rhs(double, const double *, const unsigned char *sw, const double *, double *yd) {
+        yd[0] = sw[0] ? 1.0 : -1.0;
+        yd[1] = 0.0;
+        yd[2] = 0.0;
+    }
+    static AENS_DEV void jac(double, const double *, const unsigned char *, const double *, double *) {}
+    static AENS_DEV void events(double t, const double *y, const unsigned char *, const double *, double *g) {
+        g[0] = y[1] - 1.0;
+        g[1] = -y[2] + 1.0;
+        g[2] = -t + 1.0;
+    }
+    static AENS_DEV int handle_event(double t, double *y, unsigned char *sw, const int *info_in, const double *p) {
+        int info[3] = {info_in[0], info_in[1], info_in[2]};
+        for (int iter = 0; iter < 100; ++iter) { /* event iteration, conftest.py:64-80 */
+            double b[3], a[3];
+#pragma unroll
+            for (int i = 0; i < 3; ++i) if (info[i] != 0) sw[i] = !sw[i];
+            events(t, y, sw, p, b);
+            y[1] = sw[1] ? -1.0 : 3.0;
+            y[2] = sw[2] ? 0.0 : 2.0;
+            events(t, y, sw, p, a);
+            int any = 0;
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                info[i] = ((b[i] < 0.0 && a[i] > 0.0) || (b[i] > 0.0 && a[i] < 0.0)) ? 1 : 0;
+                any |= info[i];
+            }
+            if (!any) break;
+        }
+        return 0;
+    }
+};
+
+#ifdef AENS_USER_MODEL
+/* NVRTC path: the user source defines the plain functions; dimensions arrive as -D macros. */
+struct AensUser {
+    static constexpr int N = AENS_USER_N, NP = AENS_USER_NP, NG = AENS_USER_NG, NSW = AENS_USER_NSW;
+    static constexpr bool HAS_JAC = (AENS_USER_HAS_JAC != 0);
+    static AENS_DEV void rhs(double t, const double *y, const unsigned char *sw, const double *p, double *yd) {
+        aens_rhs(t, y, sw, p, yd);
+    }
+    static AENS_DEV void jac(double t, const double *y, const unsigned char *sw, const double *p, double *J) {
+#if AENS_USER_HAS_JAC
+        aens_jac(t, y, sw, p, J);
+#endif
+    }
+    static AENS_DEV void events(double t, const double *y, const unsigned char *sw, const double *p, double *g) {
+#if AENS_USER_NG > 0
+        aens_events(t, y, sw, p, g);
+#endif
+    }
+    static AENS_DEV int handle_event(double t, double *y, unsigned char *sw, const int *info, const double *p) {
+#if AENS_USER_NG > 0
+        return aens_handle_event(t, y, sw, info, p);
+#else
+        return 0;
+#endif
+    }
+};
+#endif
+
+#endif /* AENS_MODELS_CUH */

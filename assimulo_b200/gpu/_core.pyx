@@ -1,0 +1,371 @@
+# cython: language_level=3, boundscheck=False, wraparound=False
+"""Cython host binding of libassimulo_cuda.so (include/assimulo_cuda.h).
+
+Plays the role ``thirdparty/radau5/radau5ode.pyx`` (RadauMemory + radau5_py_solve) and the f2py module
+``assimulo.lib.dopri5`` play in the reference: the only place where Python objects meet the native ABI.  The
+difference is that no callback ever crosses back into Python, so the GIL is released around every call that
+touches the device (the reference holds it throughout, SURVEY.md 8b).
+"""
+import numpy as np
+cimport numpy as np
+
+np.import_array()
+
+cdef extern from "assimulo_cuda.h":
+    int AENS_MAX_N
+    int AENS_NSTATS
+    ctypedef struct aens_opts_t:
+        int solver
+        int arith
+        int maxsteps
+        int newt
+        int usejac
+        int reserved
+        double rtol
+        double atol[16]
+        double h
+        double inith
+        double maxh
+        double safe
+        double fac1
+        double fac2
+        double beta
+        double thet
+        double fnewt
+        double quot1
+        double quot2
+    ctypedef struct aens_handle_t:
+        pass
+    int aens_default_opts(int solver, aens_opts_t *o) nogil
+    int aens_create(int device, aens_handle_t **h) nogil
+    int aens_destroy(aens_handle_t **h) nogil
+    const char *aens_last_error(const aens_handle_t *h) nogil
+    const char *aens_version() nogil
+    int aens_set_model_builtin(aens_handle_t *h, const char *name) nogil
+    int aens_set_model_source(aens_handle_t *h, const char *src, int n, int n_p, int n_g, int n_sw, int has_jac) nogil
+    int aens_model_dims(const aens_handle_t *h, int *n, int *n_p, int *n_g, int *n_sw, int *has_jac) nogil
+    int aens_set_ensemble(aens_handle_t *h, long long N, const double *y0, const double *p,
+                          const unsigned char *sw0, double t0) nogil
+    int aens_set_opts(aens_handle_t *h, const aens_opts_t *o) nogil
+    int aens_set_output(aens_handle_t *h, int n_out, const double *t_out, int event_slots) nogil
+    int aens_set_schedule(aens_handle_t *h, int refill_threshold, const int *order) nogil
+    int aens_simulate(aens_handle_t *h, double tfinal) nogil
+    int aens_simulate_async(aens_handle_t *h, double tfinal) nogil
+    int aens_sync(aens_handle_t *h) nogil
+    int aens_last_kernel_ms(aens_handle_t *h, float *ms) nogil
+    int aens_get_final(aens_handle_t *h, double *t, double *y, unsigned char *sw, int *status) nogil
+    int aens_get_stats(aens_handle_t *h, int which, int *out) nogil
+    int aens_get_stats_sum(aens_handle_t *h, long long *sums) nogil
+    int aens_get_dense(aens_handle_t *h, int slot, double *y_out) nogil
+    int aens_get_dense_all(aens_handle_t *h, double *y_out) nogil
+    int aens_get_events(aens_handle_t *h, int *count, double *t_ev, int *info) nogil
+    int aens_device_ptr(aens_handle_t *h, int which, void **ptr, long long *nbytes) nogil
+    int aens_stream(aens_handle_t *h, void **stream) nogil
+    int aens_measure_fp64_peak(int device, double seconds, double *tflops, double *mhz) nogil
+    long long aens_nvrtc_check(const char *src, int n, int n_p, int n_g, int n_sw, int has_jac, int strict,
+                               char *errbuf, int errbuf_len) nogil
+    long long aens_launch_count(const aens_handle_t *h) nogil
+
+STAT_NAMES = ("nsteps", "nfcns", "nerrfails", "njacs", "nlus", "nstatefcns", "nstateevents", "nstepstotal")
+SOLVER_IDS = {"ExplicitEuler": 0, "RungeKutta4": 1, "RungeKutta34": 2, "Dopri5": 3, "Radau5ODE": 4}
+MAX_N = 16
+
+
+class AensError(RuntimeError):
+    """Raised for a negative return code of the C ABI; carries ``code`` and the library's message."""
+    def __init__(self, code, msg):
+        RuntimeError.__init__(self, "libassimulo_cuda error %d: %s" % (code, msg))
+        self.code = code
+
+
+def version():
+    return aens_version().decode()
+
+
+def default_opts(solver):
+    """Reference defaults of `solver` (name) as a dict."""
+    cdef aens_opts_t o
+    cdef int rc = aens_default_opts(SOLVER_IDS[solver], &o)
+    if rc != 0:
+        raise AensError(rc, "unknown solver")
+    return _opts_to_dict(&o)
+
+
+cdef dict _opts_to_dict(aens_opts_t *o):
+    return dict(solver=o.solver, arith=o.arith, maxsteps=o.maxsteps, newt=o.newt, usejac=o.usejac, rtol=o.rtol,
+                atol=[o.atol[i] for i in range(16)], h=o.h, inith=o.inith, maxh=o.maxh, safe=o.safe,
+                fac1=o.fac1, fac2=o.fac2, beta=o.beta, thet=o.thet, fnewt=o.fnewt, quot1=o.quot1, quot2=o.quot2)
+
+
+def nvrtc_check(src, int n, int n_p=0, int n_g=0, int n_sw=0, bint has_jac=False, bint strict=False):
+    """Compile-only check of a CUDA model source (no GPU needed).  Returns the cubin size."""
+    cdef bytes b = src.encode() if isinstance(src, str) else src
+    cdef char err[4096]
+    cdef const char *cs = b
+    cdef long long r
+    err[0] = 0
+    with nogil:
+        r = aens_nvrtc_check(cs, n, n_p, n_g, n_sw, has_jac, strict, err, 4096)
+    if r < 0:
+        raise AensError(<int>r, err.decode(errors="replace"))
+    return r
+
+
+def measure_fp64_peak(int device=0, double seconds=1.0):
+    cdef double tf = 0.0, mhz = 0.0
+    cdef int rc
+    with nogil:
+        rc = aens_measure_fp64_peak(device, seconds, &tf, &mhz)
+    if rc != 0:
+        raise AensError(rc, "fp64 peak measurement failed (no GPU?)")
+    return tf, mhz
+
+
+cdef class Handle:
+    """One ensemble on one GPU (owns the device memory and a CUDA stream)."""
+    cdef aens_handle_t *h
+    cdef public int n, n_p, n_g, n_sw, has_jac
+    cdef public long long N
+    cdef public int n_out, event_slots
+
+    def __cinit__(self, int device=0):
+        self.h = NULL
+        cdef int rc
+        with nogil:
+            rc = aens_create(device, &self.h)
+        if rc != 0:
+            raise AensError(rc, "aens_create(device=%d) failed: no usable CUDA device (there is no CPU fallback)"
+                            % device)
+        self.N = 0
+        self.n_out = 0
+        self.event_slots = 16
+
+    def __dealloc__(self):
+        if self.h != NULL:
+            aens_destroy(&self.h)
+
+    cdef _check(self, int rc):
+        if rc < 0:
+            raise AensError(rc, aens_last_error(self.h).decode(errors="replace"))
+        return rc
+
+    def close(self):
+        if self.h != NULL:
+            aens_destroy(&self.h)
+
+    def _dims(self):
+        cdef int n, p, g, s, j
+        self._check(aens_model_dims(self.h, &n, &p, &g, &s, &j))
+        self.n, self.n_p, self.n_g, self.n_sw, self.has_jac = n, p, g, s, j
+
+    def set_model_builtin(self, name):
+        cdef bytes b = name.encode()
+        self._check(aens_set_model_builtin(self.h, b))
+        self._dims()
+
+    def set_model_source(self, src, int n, int n_p=0, int n_g=0, int n_sw=0, bint has_jac=False):
+        cdef bytes b = src.encode() if isinstance(src, str) else src
+        cdef const char *cs = b
+        cdef int rc
+        with nogil:
+            rc = aens_set_model_source(self.h, cs, n, n_p, n_g, n_sw, has_jac)
+        self._check(rc)
+        self._dims()
+
+    def set_ensemble(self, y0, p=None, sw0=None, double t0=0.0):
+        cdef np.ndarray[double, ndim=2, mode="c"] y = np.ascontiguousarray(y0, dtype=np.float64)
+        cdef np.ndarray[double, ndim=2, mode="c"] pp
+        cdef np.ndarray[np.uint8_t, ndim=2, mode="c"] ss
+        cdef const double *pptr = NULL
+        cdef const unsigned char *sptr = NULL
+        cdef long long N = y.shape[0]
+        if y.shape[1] != self.n:
+            raise ValueError("y0 must have shape [N, %d]" % self.n)
+        if self.n_p:
+            pp = np.ascontiguousarray(p, dtype=np.float64)
+            if pp.shape[0] != N or pp.shape[1] != self.n_p:
+                raise ValueError("p must have shape [N, %d]" % self.n_p)
+            pptr = &pp[0, 0]
+        if self.n_sw:
+            ss = np.ascontiguousarray(sw0, dtype=np.uint8)
+            if ss.shape[0] != N or ss.shape[1] != self.n_sw:
+                raise ValueError("sw0 must have shape [N, %d]" % self.n_sw)
+            sptr = &ss[0, 0]
+        cdef const double *yptr = &y[0, 0]
+        cdef int rc
+        with nogil:
+            rc = aens_set_ensemble(self.h, N, yptr, pptr, sptr, t0)
+        self._check(rc)
+        self.N = N
+        self.n_out = 0
+
+    def set_opts(self, dict d):
+        cdef aens_opts_t o
+        self._check(aens_default_opts(d["solver"], &o))
+        o.arith = d.get("arith", o.arith)
+        o.maxsteps = d.get("maxsteps", o.maxsteps)
+        o.newt = d.get("newt", o.newt)
+        o.usejac = d.get("usejac", o.usejac)
+        o.rtol = d.get("rtol", o.rtol)
+        atol = np.broadcast_to(np.asarray(d.get("atol", 1e-6), dtype=np.float64), (self.n,))
+        for i in range(self.n):
+            o.atol[i] = atol[i]
+        o.h = d.get("h", o.h)
+        o.inith = d.get("inith", o.inith)
+        o.maxh = d.get("maxh", o.maxh)
+        o.safe = d.get("safe", o.safe)
+        o.fac1 = d.get("fac1", o.fac1)
+        o.fac2 = d.get("fac2", o.fac2)
+        o.beta = d.get("beta", o.beta)
+        o.thet = d.get("thet", o.thet)
+        o.fnewt = d.get("fnewt", o.fnewt)
+        o.quot1 = d.get("quot1", o.quot1)
+        o.quot2 = d.get("quot2", o.quot2)
+        self._check(aens_set_opts(self.h, &o))
+
+    def set_output(self, t_out=None, int event_slots=16):
+        cdef np.ndarray[double, ndim=1, mode="c"] tg
+        cdef const double *tp = NULL
+        cdef int n_out = 0
+        if t_out is not None and len(t_out) > 0:
+            tg = np.ascontiguousarray(t_out, dtype=np.float64)
+            tp = &tg[0]
+            n_out = tg.shape[0]
+        cdef int rc
+        with nogil:
+            rc = aens_set_output(self.h, n_out, tp, event_slots)
+        self._check(rc)
+        self.n_out = n_out
+        self.event_slots = event_slots
+
+    def set_schedule(self, int refill_threshold=32, order=None):
+        cdef np.ndarray[int, ndim=1, mode="c"] od
+        cdef const int *op = NULL
+        if order is not None:
+            od = np.ascontiguousarray(order, dtype=np.intc)
+            if od.shape[0] != self.N:
+                raise ValueError("order must be a permutation of range(N)")
+            op = &od[0]
+        cdef int rc
+        with nogil:
+            rc = aens_set_schedule(self.h, refill_threshold, op)
+        self._check(rc)
+
+    def simulate(self, double tfinal):
+        cdef int rc
+        with nogil:
+            rc = aens_simulate(self.h, tfinal)
+        self._check(rc)
+
+    def simulate_async(self, double tfinal):
+        cdef int rc
+        with nogil:
+            rc = aens_simulate_async(self.h, tfinal)
+        self._check(rc)
+
+    def sync(self):
+        cdef int rc
+        with nogil:
+            rc = aens_sync(self.h)
+        self._check(rc)
+
+    def last_kernel_ms(self):
+        cdef float ms = 0
+        self._check(aens_last_kernel_ms(self.h, &ms))
+        return ms
+
+    def get_final(self, bint want_y=True, bint want_sw=True):
+        """Returns (t[N], y[N,n] or None, sw[N,n_sw] or None, status[N])."""
+        cdef np.ndarray[double, ndim=1, mode="c"] t = np.empty(self.N, dtype=np.float64)
+        cdef np.ndarray[int, ndim=1, mode="c"] st = np.empty(self.N, dtype=np.intc)
+        cdef np.ndarray[double, ndim=2, mode="c"] y
+        cdef np.ndarray[np.uint8_t, ndim=2, mode="c"] sw
+        cdef double *yp = NULL
+        cdef unsigned char *sp = NULL
+        cdef object yo = None
+        cdef object so = None
+        if want_y:
+            y = np.empty((self.N, self.n), dtype=np.float64)
+            yp = &y[0, 0]
+            yo = y
+        if want_sw and self.n_sw:
+            sw = np.empty((self.N, self.n_sw), dtype=np.uint8)
+            sp = &sw[0, 0]
+            so = sw
+        cdef double *tp = &t[0]
+        cdef int *stp = &st[0]
+        cdef int rc
+        with nogil:
+            rc = aens_get_final(self.h, tp, yp, sp, stp)
+        self._check(rc)
+        return t, yo, so, st
+
+    def get_stats(self, which):
+        cdef int w = STAT_NAMES.index(which) if isinstance(which, str) else which
+        cdef np.ndarray[int, ndim=1, mode="c"] out = np.empty(self.N, dtype=np.intc)
+        cdef int *op = &out[0]
+        cdef int rc
+        with nogil:
+            rc = aens_get_stats(self.h, w, op)
+        self._check(rc)
+        return out
+
+    def get_stats_sum(self):
+        cdef long long s[8]
+        cdef int rc
+        with nogil:
+            rc = aens_get_stats_sum(self.h, s)
+        self._check(rc)
+        return {STAT_NAMES[i]: s[i] for i in range(8)}
+
+    def get_dense(self, slot=None):
+        """Row `slot` as [N,n], or all rows as [n_out,N,n] when slot is None."""
+        cdef np.ndarray[double, ndim=3, mode="c"] a3
+        cdef np.ndarray[double, ndim=2, mode="c"] a2
+        cdef double *p
+        cdef int rc, k
+        if slot is None:
+            a3 = np.empty((self.n_out, self.N, self.n), dtype=np.float64)
+            if self.n_out == 0:
+                return a3
+            p = &a3[0, 0, 0]
+            with nogil:
+                rc = aens_get_dense_all(self.h, p)
+            self._check(rc)
+            return a3
+        a2 = np.empty((self.N, self.n), dtype=np.float64)
+        p = &a2[0, 0]
+        k = slot
+        with nogil:
+            rc = aens_get_dense(self.h, k, p)
+        self._check(rc)
+        return a2
+
+    def get_events(self):
+        """Returns (count[N], t_ev[N,slots], info[N,slots]) -- ring order, see assimulo_cuda.h."""
+        cdef int S = self.event_slots if (self.n_g > 0 and self.event_slots > 0) else 0
+        cdef np.ndarray[int, ndim=1, mode="c"] cnt = np.zeros(self.N, dtype=np.intc)
+        cdef np.ndarray[double, ndim=2, mode="c"] te = np.full((self.N, max(S, 1)), np.nan)
+        cdef np.ndarray[int, ndim=2, mode="c"] info = np.zeros((self.N, max(S, 1)), dtype=np.intc)
+        cdef int *cp = &cnt[0]
+        cdef double *tp = &te[0, 0] if S > 0 else NULL
+        cdef int *ip = &info[0, 0] if S > 0 else NULL
+        cdef int rc
+        with nogil:
+            rc = aens_get_events(self.h, cp, tp, ip)
+        self._check(rc)
+        return cnt, te[:, :S], info[:, :S]
+
+    def device_ptr(self, int which):
+        cdef void *p = NULL
+        cdef long long b = 0
+        self._check(aens_device_ptr(self.h, which, &p, &b))
+        return <size_t>p, b
+
+    def stream(self):
+        cdef void *s = NULL
+        self._check(aens_stream(self.h, &s))
+        return <size_t>s
+
+    def launch_count(self):
+        return aens_launch_count(self.h)

@@ -1,0 +1,487 @@
+"""Batched solver classes with the reference's option surface.
+
+Each class mirrors one ``Explicit_ODE`` subclass of the reference (same option names, defaults, validation
+messages and statistics keys) but integrates all N members of a Batched_Explicit_Problem in ONE kernel launch
+through libassimulo_cuda.so:
+
+    Dopri5         src/solvers/runge_kutta.py:26-428    (core thirdparty/hairer/dopri5.f)
+    RungeKutta34   src/solvers/runge_kutta.py:430-743
+    RungeKutta4    src/solvers/runge_kutta.py:746-872
+    ExplicitEuler  src/solvers/euler.pyx:485-692
+    Radau5ODE      src/solvers/radau5.py:69-430, src/lib/radau_core.py (core thirdparty/radau5/radau5.c)
+
+``simulate(tfinal, ncp)`` follows ODE.simulate (src/ode.pyx:192-332): output grid ``linspace(t0, tfinal, ncp+1)[1:]``
+(or ``ncp_list``), continuation from the current time on a second call, statistics reset per call.  It returns
+``(t_sol, y_sol)`` with ``y_sol[k]`` of shape ``[N, n]``; with ``ncp=0`` the rows are the initial and the final
+state (the members' internal steps differ, so there is no common internal grid to report).
+
+There is no CPU fallback: creating the device handle raises if no CUDA device is usable.
+"""
+import numpy as np
+
+from .exception import (AssimuloException, Dopri5_Exception, Explicit_ODE_Exception, Radau_Exception)
+from .problem import Batched_Explicit_Problem
+
+ARITH = {"strict": 0, "fast": 1}
+STAT_NAMES = ("nsteps", "nfcns", "nerrfails", "njacs", "nlus", "nstatefcns", "nstateevents", "nstepstotal")
+
+# status codes (include/assimulo_cuda.h)
+ST_COMPLETE, ST_TERMINATED = 0, 1
+
+
+def _core():
+    from . import _core as c  # the Cython module; import lazily so that option handling works without it
+    return c
+
+
+class Statistics(dict):
+    """Totals over the ensemble under the reference's key names (src/support.pyx:33-83, src/ode.pyx:153-172);
+    ``per_member(key)`` gives the int32 array over members."""
+
+    def __init__(self, solver):
+        dict.__init__(self, {k: 0 for k in STAT_NAMES})
+        self._solver = solver
+
+    def reset(self):
+        for k in self:
+            self[k] = 0
+
+    def per_member(self, key):
+        return self._solver._stats_per_member(key)
+
+
+class Batched_Explicit_ODE(object):
+    """Base class: the batched counterpart of Explicit_ODE (src/explicit_ode.pyx:69-135) + ODE (src/ode.pyx)."""
+    _solver_name = None
+    _exc = Explicit_ODE_Exception
+
+    def __init__(self, problem, device=None, comm=None):
+        if not isinstance(problem, Batched_Explicit_Problem):
+            raise Explicit_ODE_Exception("The problem needs to be a subclass of a Batched_Explicit_Problem.")
+        self.problem = problem
+        self.options = {"arith": "fast", "refill_threshold": 32, "order": None, "event_slots": 16,
+                        "verbosity": 30, "store_event_points": True}
+        self.supports = {"state_events": False, "interpolated_output": False, "report_continuously": False}
+        self.problem_info = {"dim": problem.n, "dimRoot": problem.n_g, "state_events": problem.n_g > 0,
+                             "jac_fcn": problem.has_jac, "switches": problem.n_sw > 0}
+        self.statistics = Statistics(self)
+        self._device = device
+        self._comm = comm          # a parallel.Shard describing this rank's block, or None
+        self._handle = None
+        self._leny = problem.n
+        self._dirty = True         # ensemble must be (re)uploaded
+        self._launched = False
+        self.t0 = problem.t0
+        self.t = problem.t0
+        self.N = problem.N
+        self.y = problem.y0.copy()
+        self.sw = problem.sw0.astype(bool)
+        self.status = np.zeros(self.N, dtype=np.intc)
+        self.t_members = np.full(self.N, problem.t0)
+        self.t_sol, self.y_sol = [], []
+        self.elapsed_kernel_ms = None
+
+    # ---- device plumbing -------------------------------------------------------------------------
+    def _get_handle(self):
+        if self._handle is None:
+            c = _core()
+            dev = self._device
+            if dev is None:
+                dev = 0
+            self._handle = c.Handle(int(dev))
+            if self.problem.model is not None:
+                self._handle.set_model_builtin(self.problem.model)
+            else:
+                p = self.problem
+                self._handle.set_model_source(p.source, p.n, p.n_p, p.n_g, p.n_sw, p.has_jac)
+        return self._handle
+
+    def _opts_dict(self):
+        c = _core()
+        d = {"solver": c.SOLVER_IDS[self._solver_name], "arith": ARITH[self.options["arith"]]}
+        for k in ("maxsteps", "newt", "rtol", "h", "inith", "safe", "fac1", "fac2", "beta", "thet", "quot1", "quot2"):
+            if k in self.options and self.options[k] is not None:
+                d[k] = self.options[k]
+        if "atol" in self.options:
+            d["atol"] = np.asarray(self.options["atol"], dtype=np.float64)
+        if self.options.get("fnewt"):
+            d["fnewt"] = self.options["fnewt"]
+        maxh = self.options.get("maxh")
+        if maxh is not None and np.isfinite(maxh):
+            d["maxh"] = maxh  # inf / None -> 0 = unset (dopri5.f:301-305, radau5.c:210-212)
+        if "usejac" in self.options:
+            d["usejac"] = int(bool(self.options["usejac"]))
+        return d
+
+    def _stats_per_member(self, key):
+        if self._handle is None or not self._launched:
+            return np.zeros(self.N, dtype=np.intc)
+        return self._handle.get_stats(key)
+
+    # ---- reference surface ------------------------------------------------------------------------
+    def re_init(self, t0, y0, sw0=None):
+        """Reinitiates the solver (src/explicit_ode.pyx:108-135)."""
+        y0 = np.asarray(y0, dtype=np.float64)
+        if y0.shape[-1] != self._leny:
+            raise Explicit_ODE_Exception("y0 must be of the same length as the original problem.")
+        self.t = float(t0)
+        self.y = np.ascontiguousarray(np.broadcast_to(y0.reshape(-1, self._leny), (self.N, self._leny))).copy()
+        if sw0 is not None:
+            self.sw = np.ascontiguousarray(np.broadcast_to(np.asarray(sw0, dtype=bool).reshape(-1, self.problem.n_sw),
+                                                           (self.N, self.problem.n_sw))).copy()
+        self.t_members = np.full(self.N, self.t)
+        self._dirty = True
+
+    def reset(self):
+        self.re_init(self.problem.t0, self.problem.y0, self.problem.sw0 if self.problem.n_sw else None)
+
+    def initialize(self):
+        self.statistics.reset()
+
+    def finalize(self):
+        pass
+
+    def simulate(self, tfinal, ncp=0, ncp_list=None):
+        t0 = self.t
+        self.t_sol, self.y_sol = [], []
+        try:
+            tfinal = float(tfinal)
+        except (ValueError, TypeError):
+            raise AssimuloException("Final time must be an integer or float.")
+        if self.t > tfinal:
+            raise AssimuloException("Final time {} must be greater than start time {}.\n Perhaps you should consider "
+                                    "to reset the integration.".format(tfinal, self.t))
+        if not isinstance(ncp, int):
+            raise AssimuloException("Number of communication points must be an integer")
+        if ncp < 0:
+            ncp = 0
+        if (ncp != 0 or ncp_list is not None) and not self.supports["interpolated_output"]:
+            ncp, ncp_list = 0, None  # e.g. RungeKutta4 (src/ode.pyx:260-263)
+        if ncp != 0:
+            output_list = np.linspace(t0, tfinal, ncp + 1)[1:]
+        elif ncp_list is not None:
+            nl = np.array(ncp_list, dtype=float, ndmin=1)
+            output_list = nl[np.logical_and(nl > t0, nl <= tfinal)]
+            if len(output_list) == 0 or output_list[-1] < tfinal:
+                output_list = np.append(output_list, tfinal)
+        else:
+            output_list = None
+
+        self.problem.initialize(self)
+        self.initialize()
+        h = self._get_handle()
+        if self._dirty:
+            h.set_ensemble(self.y, self.problem.p0 if self.problem.n_p else None,
+                           self.sw.astype(np.uint8) if self.problem.n_sw else None, self.t)
+            self._dirty = False
+        h.set_opts(self._opts_dict())
+        h.set_output(output_list, int(self.options["event_slots"]))
+        h.set_schedule(int(self.options["refill_threshold"]), self.options["order"])
+        self.problem.handle_result(self, t0, self.y.copy())
+        h.simulate(tfinal)
+        self._launched = True
+        self.elapsed_kernel_ms = h.last_kernel_ms()
+        tm, y, sw, status = h.get_final()
+        self.t_members, self.y, self.status = tm, y, status
+        if sw is not None:
+            self.sw = sw.astype(bool)
+        sums = h.get_stats_sum()
+        for k in STAT_NAMES:
+            self.statistics[k] = int(sums[k])
+        if output_list is not None:
+            dense = h.get_dense()
+            for k, tk in enumerate(output_list):
+                self.problem.handle_result(self, float(tk), dense[k])
+        else:
+            self.problem.handle_result(self, tfinal, self.y.copy())
+        # the ensemble's current time: members that failed or were terminated stopped early (see status)
+        self.t = tfinal if np.all(self.status == ST_COMPLETE) else float(np.min(self.t_members))
+        if self.problem.n_g > 0:
+            self._events = h.get_events()
+        self.finalize()
+        self.problem.finalize(self)
+        return self.t_sol, np.array(self.y_sol)
+
+    __call__ = simulate
+
+    @property
+    def event_log(self):
+        """(count[N], t_event[N, slots], info[N, slots]): ring of the last `event_slots` state events of each
+        member.  info bit 2i: indicator i fired; bit 2i+1: event_info[i] == +1 (else -1), cf.
+        src/explicit_ode.pyx:351-357."""
+        return getattr(self, "_events", (np.zeros(self.N, dtype=np.intc), np.zeros((self.N, 0)),
+                                         np.zeros((self.N, 0), dtype=np.intc)))
+
+    def event_times(self, member):
+        """Chronological event times of one member (at most `event_slots` most recent)."""
+        cnt, te, _ = self.event_log
+        c, S = int(cnt[member]), te.shape[1]
+        if S == 0 or c == 0:
+            return np.zeros(0)
+        idx = [(e % S) for e in range(max(0, c - S), c)]
+        return te[member, idx]
+
+    def get_options(self):
+        return self.options.copy()
+
+    def print_statistics(self, verbose=30):
+        print("Final Run Statistics: %s (%d members)\n" % (self.problem.name, self.N))
+        for k in STAT_NAMES:
+            print(" %-22s : %d" % (k, self.statistics[k]))
+        print("\nSolver options:\n\n Solver                  : %s (batched, %s arithmetic)" %
+              (self._solver_name, self.options["arith"]))
+
+    # ---- options shared by all batched solvers ------------------------------------------------------
+    def _get_arith(self):
+        """'fast' (FMA contraction, fp32 step-size-controller powers) or 'strict' (reference operation order,
+        no contraction: reproduces the CPU reference step for step)."""
+        return self.options["arith"]
+
+    def _set_arith(self, v):
+        if v not in ARITH:
+            raise AssimuloException("arith must be 'fast' or 'strict'.")
+        self.options["arith"] = v
+    arith = property(_get_arith, _set_arith)
+
+    def _get_refill(self):
+        """A warp fetches new members once this many of its 32 lanes are idle (1..32)."""
+        return self.options["refill_threshold"]
+
+    def _set_refill(self, v):
+        v = int(v)
+        if not 1 <= v <= 32:
+            raise AssimuloException("refill_threshold must be in 1..32.")
+        self.options["refill_threshold"] = v
+    refill_threshold = property(_get_refill, _set_refill)
+
+    def _get_order(self):
+        """Optional permutation of range(N): the order in which members are handed to the warps."""
+        return self.options["order"]
+
+    def _set_order(self, v):
+        self.options["order"] = None if v is None else np.ascontiguousarray(v, dtype=np.intc)
+    order = property(_get_order, _set_order)
+
+    def _get_event_slots(self):
+        return self.options["event_slots"]
+
+    def _set_event_slots(self, v):
+        self.options["event_slots"] = int(v)
+    event_slots = property(_get_event_slots, _set_event_slots)
+
+    # helpers for the option properties below
+    def _float_opt(self, key, value, msg):
+        try:
+            self.options[key] = float(value)
+        except (ValueError, TypeError):
+            raise self._exc(msg)
+
+    def _set_atol_common(self, atol):
+        a = np.array(atol, dtype=float) if len(np.array(atol, dtype=float).shape) > 0 else np.array([atol], dtype=float)
+        if len(a) == 1:
+            a = a * np.ones(self._leny)
+        elif len(a) != self._leny:
+            raise self._exc("atol must be of length one or same as the dimension of the problem.")
+        self.options["atol"] = a
+
+    def _set_rtol_common(self, rtol):
+        try:
+            r = float(rtol)
+        except (ValueError, TypeError):
+            raise self._exc("Relative tolerance must be a (scalar) float.")
+        if r <= 0.0:
+            raise self._exc("Relative tolerance must be a positive (scalar) float.")
+        self.options["rtol"] = r
+
+    def _set_maxsteps_common(self, max_steps):
+        try:
+            max_steps = int(max_steps)
+        except (TypeError, ValueError):
+            raise self._exc("Maximum number of steps must be a positive integer.")
+        self.options["maxsteps"] = max_steps
+
+
+def _prop(key, setter=None, doc=None):
+    def g(self):
+        return self.options[key]
+
+    def s(self, v):
+        if setter is None:
+            self.options[key] = v
+        else:
+            setter(self, v)
+    return property(g, s, doc=doc)
+
+
+class _FixedStep(Batched_Explicit_ODE):
+    def _set_h(self, h):
+        try:
+            self.options["h"] = float(h)
+        except Exception:
+            raise AssimuloException("Step-size must be a (scalar) float.")
+    h = _prop("h", _set_h, "Fixed step-size, default 0.01 (runge_kutta.py:784, euler.pyx:522).")
+
+
+class ExplicitEuler(_FixedStep):
+    """Explicit Euler with state events and linear dense output (src/solvers/euler.pyx:485-692)."""
+    _solver_name = "ExplicitEuler"
+
+    def __init__(self, problem, **kw):
+        Batched_Explicit_ODE.__init__(self, problem, **kw)
+        self.options["h"] = 0.01
+        self.supports.update(report_continuously=True, interpolated_output=True, state_events=True)
+
+
+class RungeKutta4(_FixedStep):
+    """Classical RK4, fixed step; no events, no interpolated output (src/solvers/runge_kutta.py:746-872)."""
+    _solver_name = "RungeKutta4"
+
+    def __init__(self, problem, **kw):
+        Batched_Explicit_ODE.__init__(self, problem, **kw)
+        self.options["h"] = 0.01
+
+
+class RungeKutta34(Batched_Explicit_ODE):
+    """Adaptive RK of order four, no step rejection (src/solvers/runge_kutta.py:430-743)."""
+    _solver_name = "RungeKutta34"
+
+    def __init__(self, problem, **kw):
+        Batched_Explicit_ODE.__init__(self, problem, **kw)
+        self.options.update(atol=1.0e-6 * np.ones(self._leny), rtol=1.0e-6, inith=0.01, maxsteps=10000)
+        self.supports.update(report_continuously=True, interpolated_output=True, state_events=True)
+
+    def _set_inith(self, v):
+        try:
+            self.options["inith"] = float(v)
+        except (ValueError, TypeError):
+            raise Explicit_ODE_Exception("Initial step must be an integer or float.")
+
+    def _set_atol(self, atol):
+        try:
+            a = np.array(atol, dtype=float)
+        except (ValueError, TypeError):
+            raise Explicit_ODE_Exception("Absolute tolerance must be a positive float or a float vector.")
+        if a.ndim == 0:
+            a = a * np.ones(self._leny)
+        if len(a) != self._leny or (a <= 0.0).any():
+            raise Explicit_ODE_Exception("Absolute tolerance must be a positive float or a float vector.")
+        self.options["atol"] = a
+
+    def _set_rtol(self, rtol):
+        try:
+            r = float(rtol)
+        except (TypeError, ValueError):
+            raise Explicit_ODE_Exception("Relative tolerance must be a float.")
+        if r <= 0.0:
+            raise Explicit_ODE_Exception("Relative tolerance must be a positive (scalar) float.")
+        self.options["rtol"] = r
+
+    inith = _prop("inith", _set_inith, "Initial step-size, default 0.01.")
+    atol = _prop("atol", _set_atol, "Absolute tolerance(s), default 1e-6.")
+    rtol = _prop("rtol", _set_rtol, "Relative tolerance, default 1e-6.")
+    maxsteps = _prop("maxsteps", Batched_Explicit_ODE._set_maxsteps_common, "Maximum number of steps, default 10000.")
+
+
+class Dopri5(Batched_Explicit_ODE):
+    """Dormand-Prince 5(4) with Hairer's step-size control and dense output
+    (src/solvers/runge_kutta.py:26-428 over thirdparty/hairer/dopri5.f)."""
+    _solver_name = "Dopri5"
+    _exc = Dopri5_Exception
+
+    def __init__(self, problem, **kw):
+        Batched_Explicit_ODE.__init__(self, problem, **kw)
+        self.options.update(safe=0.9, fac1=0.2, fac2=10.0, beta=0.04, maxh=np.inf, inith=0.0,
+                            atol=1.0e-6 * np.ones(self._leny), rtol=1.0e-6, maxsteps=100000)
+        self.supports.update(report_continuously=True, interpolated_output=True, state_events=True)
+
+    atol = _prop("atol", Batched_Explicit_ODE._set_atol_common, "Absolute tolerance(s), default 1e-6.")
+    rtol = _prop("rtol", Batched_Explicit_ODE._set_rtol_common, "Relative tolerance, default 1e-6.")
+    maxsteps = _prop("maxsteps", Batched_Explicit_ODE._set_maxsteps_common, "Maximum number of steps, default 100000.")
+    fac1 = _prop("fac1", lambda s, v: s._float_opt("fac1", v, "The fac1 must be an integer or float."),
+                 "Lower bound of the step-size ratio, default 0.2.")
+    fac2 = _prop("fac2", lambda s, v: s._float_opt("fac2", v, "The fac2 must be an integer or float."),
+                 "Upper bound of the step-size ratio, default 10.")
+    safe = _prop("safe", lambda s, v: s._float_opt("safe", v, "The safe must be an integer or float."),
+                 "Safety factor, default 0.9.")
+    beta = _prop("beta", lambda s, v: s._float_opt("beta", v, "The beta must be an integer or float."),
+                 "Stabilisation of the step-size controller, default 0.04.")
+    inith = _prop("inith", lambda s, v: s._float_opt("inith", v, "The initial step must be an integer or float."),
+                  "Initial step-size; 0 lets HINIT choose (default).")
+
+    def _set_maxh(self, v):
+        try:
+            self.options["maxh"] = float(v)
+        except (ValueError, TypeError):
+            raise Dopri5_Exception("Maximal stepsize must be a (scalar) float.")
+        if self.options["maxh"] < 0:
+            raise Dopri5_Exception("Maximal stepsize must be a positiv (scalar) float.")
+    maxh = _prop("maxh", _set_maxh, "Maximal step-size, default inf.")
+
+
+class Radau5ODE(Batched_Explicit_ODE):
+    """Radau IIA(5), 3 stages, simplified Newton with per-member dense LU
+    (src/solvers/radau5.py:69-430, src/lib/radau_core.py, core thirdparty/radau5/radau5.c)."""
+    _solver_name = "Radau5ODE"
+    _exc = Radau_Exception
+
+    def __init__(self, problem, **kw):
+        Batched_Explicit_ODE.__init__(self, problem, **kw)
+        self.options.update(inith=0.01, newt=7, thet=1.e-3, fnewt=None, quot1=1.0, quot2=1.2, fac1=0.2, fac2=8.0,
+                            maxh=None, safe=0.9, atol=1.0e-6 * np.ones(self._leny), rtol=1.0e-6,
+                            usejac=bool(problem.has_jac), maxsteps=100000, linear_solver="DENSE")
+        self.supports.update(report_continuously=True, interpolated_output=True, state_events=True)
+
+    def _set_newt(self, v):
+        try:
+            self.options["newt"] = int(v)
+        except (ValueError, TypeError):
+            raise Radau_Exception("The attribute 'newt' must be an integer or float.")
+
+    def _set_maxh(self, v):
+        try:
+            self.options["maxh"] = float(v)
+        except (ValueError, TypeError):
+            raise Radau_Exception("Maximal stepsize must be a (scalar) float.")
+        if self.options["maxh"] < 0:
+            raise Radau_Exception("Maximal stepsize must be a positiv (scalar) float.")
+
+    def _set_usejac(self, v):
+        if v and not self.problem.has_jac:
+            raise Radau_Exception("Use of an analytical Jacobian is enabled, but problem does contain a 'jac' function.")
+        self.options["usejac"] = bool(v)
+
+    def _set_linear_solver(self, v):
+        try:
+            up = v.upper()
+        except Exception:
+            raise Radau_Exception("'linear_solver' parameter needs to be the STRING 'DENSE' or 'SPARSE'. "
+                                  "Set value: {}, type: {}".format(v, type(v)))
+        if up not in ("DENSE", "SPARSE"):
+            raise Radau_Exception("'linear_solver' parameter needs to be either 'DENSE' or 'SPARSE'. Set value: {}".format(v))
+        if up == "SPARSE":
+            raise Radau_Exception("The batched Radau5ODE only provides the dense per-member LU (SuperLU is out of scope).")
+        self.options["linear_solver"] = up
+
+    atol = _prop("atol", Batched_Explicit_ODE._set_atol_common, "Absolute tolerance(s), default 1e-6.")
+    rtol = _prop("rtol", Batched_Explicit_ODE._set_rtol_common, "Relative tolerance, default 1e-6.")
+    maxsteps = _prop("maxsteps", Batched_Explicit_ODE._set_maxsteps_common, "Maximum number of steps, default 100000.")
+    newt = _prop("newt", _set_newt, "Maximal number of Newton iterations, default 7.")
+    maxh = _prop("maxh", _set_maxh, "Maximal step-size; None = tfinal - t.")
+    usejac = _prop("usejac", _set_usejac, "Use the model's analytic Jacobian instead of finite differences.")
+    linear_solver = _prop("linear_solver", _set_linear_solver, "'DENSE' only.")
+    inith = _prop("inith", lambda s, v: s._float_opt("inith", v, "The initial step must be an integer or float."),
+                  "Initial step-size, default 0.01.")
+    fnewt = _prop("fnewt", lambda s, v: s._float_opt("fnewt", v, "The attribute 'fnewt' must be an integer or float."),
+                  "Stopping criterion of the Newton iteration; None/0 = automatic.")
+    safe = _prop("safe", lambda s, v: s._float_opt("safe", v, "The attribute 'safe' must be an integer or float."),
+                 "Safety factor, default 0.9.")
+    thet = _prop("thet", lambda s, v: s._float_opt("thet", v, "The attribute 'thet' must be an integer or float."),
+                 "Jacobian recomputation threshold, default 1e-3.")
+    quot1 = _prop("quot1", lambda s, v: s._float_opt("quot1", v, "The attribute 'quot1' must be an integer or float."),
+                  "If quot1 < hnew/hold < quot2 the step size is kept, default 1.0.")
+    quot2 = _prop("quot2", lambda s, v: s._float_opt("quot2", v, "The attribute 'quot2' must be an integer or float."),
+                  "See quot1, default 1.2.")
+    fac1 = _prop("fac1", lambda s, v: s._float_opt("fac1", v, "The attribute 'fac1' must be an integer or float."),
+                 "Lower bound of the step-size ratio, default 0.2.")
+    fac2 = _prop("fac2", lambda s, v: s._float_opt("fac2", v, "The attribute 'fac2' must be an integer or float."),
+                 "Upper bound of the step-size ratio, default 8.")

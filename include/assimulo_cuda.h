@@ -1,0 +1,181 @@
+/*
+ * assimulo_cuda.h -- C ABI of libassimulo_cuda.so, the B200 (sm_100a) ensemble integrator behind Assimulo's
+ * Explicit_Problem + solver.simulate() surface.
+ *
+ * The reference has no single native plugin ABI for this path; it has three, and this header
+ * replaces all of them for the batched path.  Each entry point cites the reference interface it stands in for
+ * (paths relative to the reference tree):
+ *
+ *   aens_create / aens_destroy          radau_setup_mem / radau_free_mem       thirdparty/radau5/radau5_io.h:7-9
+ *   aens_set_model_* / aens_set_ensemble  the callbacks + y0 that Explicit_Problem carries: FP_CB_f, FP_CB_jac
+ *                                        (thirdparty/radau5/radau5_impl.h:26-29), FP_event_func
+ *                                        (src/ode_event_locator.h:8-9), fcn of thirdparty/hairer/dopri5.pyf:6-13
+ *   aens_set_opts                       radau_set_* setters (radau5_io.h:14-34) and the WORK/IWORK packing of
+ *                                        Dopri5.integrate (src/solvers/runge_kutta.py:146-161)
+ *   aens_simulate                       radau5_solve (thirdparty/radau5/radau5.h:6-13), dopri5()
+ *                                        (dopri5.pyf:31-50), f_event_locator (src/ode_event_locator.h:11-18) and
+ *                                        the segment loop Explicit_ODE._simulate (src/explicit_ode.pyx:137-274),
+ *                                        for ALL members in one launch
+ *   aens_get_final / aens_get_stats     (x, y, idid, iwork[16..19]) of dopri5(); radau_get_stats (radau5_io.h:11)
+ *   aens_get_dense                      contd5 (dopri5.pyf:51-61), radau_get_cont_output (radau5.h:15)
+ *   aens_get_events                     event_info / t_event returned by Explicit_ODE.event_locator
+ *                                        (src/explicit_ode.pyx:332-361)
+ *   aens_last_error                     radau_get_err_msg (radau5_io.h:12)
+ *
+ * Conventions kept from the reference's C API: int return (0 ok, >0 informational, <0 error); an opaque handle
+ * owns all device memory, the caller owns every host array; error text is retrievable from the handle; one handle =
+ * one CUDA stream = not thread-safe.  New: no callback ever crosses the boundary -- right-hand sides, Jacobians,
+ * event functions and handle_event are CUDA device functions (built-in model library or NVRTC-compiled source).
+ * There is NO CPU fallback: every compute entry point fails with AENS_ERR_CUDA when no usable GPU is present.
+ *
+ * Host array layout: member-major ("AoS") y[N][n], p[N][n_p], sw[N][n_sw] exactly like a Python loop over
+ * Explicit_Problem(rhs_i, y0_i) would hold them; the library transposes to its SoA device layout.
+ */
+#ifndef ASSIMULO_CUDA_H
+#define ASSIMULO_CUDA_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AENS_MAX_N 16   /* state dimension limit of the register-resident kernels */
+#define AENS_MAX_P 16
+#define AENS_MAX_G 8
+#define AENS_MAX_SW 8
+
+/* return codes */
+#define AENS_OK 0
+#define AENS_ERR_ARG (-1)            /* inconsistent input (cf. RADAU_ERROR_INCONSISTENT_INPUT = -2) */
+#define AENS_ERR_CUDA (-2)           /* CUDA runtime / driver failure or no GPU */
+#define AENS_ERR_NVRTC (-3)          /* model source failed to compile; text in aens_last_error */
+#define AENS_ERR_STATE (-4)          /* call order violated (e.g. simulate before set_ensemble) */
+#define AENS_ERR_UNSUPPORTED (-5)    /* model/solver combination not available */
+
+/* solver ids (the five Explicit_ODE subclasses of BASELINE.json) */
+#define AENS_SOLVER_EULER 0          /* src/solvers/euler.pyx:485 ExplicitEuler */
+#define AENS_SOLVER_RK4 1            /* src/solvers/runge_kutta.py:746 RungeKutta4 */
+#define AENS_SOLVER_RK34 2           /* src/solvers/runge_kutta.py:430 RungeKutta34 */
+#define AENS_SOLVER_DOPRI5 3         /* src/solvers/runge_kutta.py:26 Dopri5 */
+#define AENS_SOLVER_RADAU5 4         /* src/solvers/radau5.py:69 Radau5ODE */
+
+/* per-member status written by aens_simulate (aens_get_final) */
+#define AENS_ST_COMPLETE 0           /* reached tfinal (ID_PY_COMPLETE) */
+#define AENS_ST_TERMINATED 1         /* handle_event asked to stop (TerminateSimulation) */
+#define AENS_ST_MAXSTEPS (-2)        /* DOPRI5 IDID=-2 / RK34 'Final time not reached' */
+#define AENS_ST_STEP_TOO_SMALL (-3)  /* DOPRI5 IDID=-3 */
+#define AENS_ST_RADAU_NMAX (-5)      /* RADAU_ERROR_NMAX_TOO_SMALL */
+#define AENS_ST_RADAU_STEP_TOO_SMALL (-6)
+#define AENS_ST_RADAU_SINGULAR (-7)
+
+/* statistics slots for aens_get_stats (names: src/ode.pyx:153-172) */
+#define AENS_STAT_NSTEPS 0           /* accepted steps */
+#define AENS_STAT_NFCNS 1
+#define AENS_STAT_NERRFAILS 2
+#define AENS_STAT_NJACS 3
+#define AENS_STAT_NLUS 4
+#define AENS_STAT_NSTATEFCNS 5
+#define AENS_STAT_NSTATEEVENTS 6
+#define AENS_STAT_NSTEPSTOTAL 7      /* step attempts (DOPRI5 NSTEP, Radau nsteps) */
+#define AENS_NSTATS 8
+
+/* arithmetic mode */
+#define AENS_ARITH_STRICT 0  /* reference operation order, no FMA contraction, fp64 pow/sqrt/div everywhere */
+#define AENS_ARITH_FAST 1    /* FMA contraction; step-size controller powers via fp32 MUFU; same accept test */
+
+typedef struct {
+    int solver;          /* AENS_SOLVER_* */
+    int arith;           /* AENS_ARITH_* */
+    int maxsteps;        /* Dopri5/Radau5ODE: 100000, RungeKutta34: 10000 */
+    int newt;            /* Radau5ODE: max Newton iterations (7) */
+    int usejac;          /* Radau5ODE: 1 = model's analytic Jacobian, 0 = finite differences */
+    int reserved;
+    double rtol;         /* scalar, broadcast to n (runge_kutta.py:172, radau5.py:374) */
+    double atol[AENS_MAX_N];
+    double h;            /* ExplicitEuler / RungeKutta4 fixed step (0.01) */
+    double inith;        /* Dopri5: 0 => HINIT; RungeKutta34, Radau5ODE: 0.01 */
+    double maxh;         /* 0 => unset (Dopri5: inf; Radau5ODE: tfinal - t) */
+    double safe, fac1, fac2, beta;
+    double thet, fnewt /* 0 => automatic */, quot1, quot2;
+} aens_opts_t;
+
+typedef struct aens_handle_s aens_handle_t;
+
+/* fills *o with the reference's defaults for `solver` (runge_kutta.py:56-64,449-452,784; euler.pyx:522;
+ * radau5.py:99-113) */
+int aens_default_opts(int solver, aens_opts_t *o);
+
+int aens_create(int device, aens_handle_t **h);
+int aens_destroy(aens_handle_t **h);
+const char *aens_last_error(const aens_handle_t *h);
+const char *aens_version(void);
+
+/* Models.  Built-ins: "vdp" "ball" "robertson" "gyro" "linear" "linear_ev" "extended".
+ * aens_set_model_source compiles `cuda_src` with NVRTC for sm_100a.  The source must define
+ *   __device__ void aens_rhs(double t, const double* y, const unsigned char* sw, const double* p, double* yd);
+ * and, when the corresponding flag/count says so,
+ *   __device__ void aens_jac(double t, const double* y, const unsigned char* sw, const double* p, double* J_colmajor);
+ *   __device__ void aens_events(double t, const double* y, const unsigned char* sw, const double* p, double* g);
+ *   __device__ int  aens_handle_event(double t, double* y, unsigned char* sw, const int* event_info, const double* p);
+ * (handle_event returns non-zero to terminate the member). */
+int aens_set_model_builtin(aens_handle_t *h, const char *name);
+int aens_set_model_source(aens_handle_t *h, const char *cuda_src, int n, int n_p, int n_g, int n_sw, int has_jac);
+int aens_model_dims(const aens_handle_t *h, int *n, int *n_p, int *n_g, int *n_sw, int *has_jac);
+
+/* Ensemble of N members: y0[N][n], p[N][n_p] (may be NULL if n_p==0), sw0[N][n_sw] (NULL if n_sw==0), common t0.
+ * Resets every member to (t0, y0, sw0) and clears statistics and event logs. */
+int aens_set_ensemble(aens_handle_t *h, long long N, const double *y0, const double *p,
+                      const unsigned char *sw0, double t0);
+int aens_set_opts(aens_handle_t *h, const aens_opts_t *o);
+
+/* Output: n_out grid times shared by all members (ODE.simulate's output_list, src/ode.pyx:273-287);
+ * n_out = 0 => final state only.  event_slots = per-member ring size of the event log. */
+int aens_set_output(aens_handle_t *h, int n_out, const double *t_out, int event_slots);
+
+/* Scheduling of members onto persistent warps: a warp fetches new members when >= refill_threshold of its 32
+ * lanes are idle (32 = warp-granular chunks, 1 = refill every finished lane at once); `order` (may be NULL) is a
+ * permutation of 0..N-1 giving the fetch order (e.g. most expensive first). */
+int aens_set_schedule(aens_handle_t *h, int refill_threshold, const int *order);
+
+/* Integrates every member from its current time to tfinal (continuation semantics of ODE.simulate,
+ * src/ode.pyx:195-196,222).  Synchronous.  Returns AENS_OK even if individual members failed: see status[]. */
+int aens_simulate(aens_handle_t *h, double tfinal);
+/* Same, asynchronous on the handle's stream; pair with aens_sync. */
+int aens_simulate_async(aens_handle_t *h, double tfinal);
+int aens_sync(aens_handle_t *h);
+/* device time of the last aens_simulate[_async] launch in milliseconds (CUDA events on the handle's stream) */
+int aens_last_kernel_ms(aens_handle_t *h, float *ms);
+
+/* Results (any pointer may be NULL): t[N], y[N][n], sw[N][n_sw], status[N]. */
+int aens_get_final(aens_handle_t *h, double *t, double *y, unsigned char *sw, int *status);
+int aens_get_stats(aens_handle_t *h, int which, int *out /*[N]*/);
+int aens_get_stats_sum(aens_handle_t *h, long long *sums /*[AENS_NSTATS]*/);
+/* dense output row `slot` (0..n_out-1) as y_out[N][n]; rows beyond a member's end time are NaN */
+int aens_get_dense(aens_handle_t *h, int slot, double *y_out);
+/* whole buffer, y_out[n_out][N][n] */
+int aens_get_dense_all(aens_handle_t *h, double *y_out);
+/* event log: count[N] = events seen; t_ev[N][event_slots], info[N][event_slots] hold the last
+ * min(count,event_slots) events of each member in ring order (event e sits in slot e % event_slots);
+ * info bit 2i = indicator i fired, bit 2i+1 = its event_info is +1 (else -1). */
+int aens_get_events(aens_handle_t *h, int *count, double *t_ev, int *info);
+
+/* Raw device pointers (SoA, for zero-copy consumers such as an NCCL all-gather of final states):
+ * which = 0: t[N]  1: y[n][N]  2: status[N] (int)  3: stats[AENS_NSTATS][N] (int)  4: ev_t[slots][N]
+ *         5: ev_info[slots][N] (int)  6: dense[n_out][n][N]  7: p[n_p][N]  8: sw[n_sw][N] (uint8) */
+int aens_device_ptr(aens_handle_t *h, int which, void **ptr, long long *bytes);
+/* CUDA stream of the handle (cudaStream_t as void*) */
+int aens_stream(aens_handle_t *h, void **stream);
+
+/* Measurement helpers (not on the product path): sustained fp64 FMA throughput of the device measured with a
+ * dependent-chain DFMA kernel for ~`seconds`; result in TFLOP/s (2 flops per DFMA). */
+int aens_measure_fp64_peak(int device, double seconds, double *tflops, double *sm_clock_mhz_est);
+/* compile-only check of a model source with NVRTC for sm_100a (needs no GPU); returns the cubin size in bytes
+ * (> 0) or a negative AENS_ERR_* with the compiler log in errbuf */
+long long aens_nvrtc_check(const char *cuda_src, int n, int n_p, int n_g, int n_sw, int has_jac, int strict,
+                           char *errbuf, int errbuf_len);
+/* number of kernel launches issued by this handle since creation */
+long long aens_launch_count(const aens_handle_t *h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ASSIMULO_CUDA_H */
