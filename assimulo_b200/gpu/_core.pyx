@@ -47,6 +47,7 @@ cdef extern from "assimulo_cuda.h":
     int aens_set_ensemble(aens_handle_t *h, long long N, const double *y0, const double *p,
                           const unsigned char *sw0, double t0) nogil
     int aens_set_opts(aens_handle_t *h, const aens_opts_t *o) nogil
+    int aens_reset(aens_handle_t *h) nogil
     int aens_set_output(aens_handle_t *h, int n_out, const double *t_out, int event_slots) nogil
     int aens_set_schedule(aens_handle_t *h, int refill_threshold, const int *order) nogil
     int aens_simulate(aens_handle_t *h, double tfinal) nogil
@@ -65,6 +66,8 @@ cdef extern from "assimulo_cuda.h":
     long long aens_nvrtc_check(const char *src, int n, int n_p, int n_g, int n_sw, int has_jac, int strict,
                                char *errbuf, int errbuf_len) nogil
     long long aens_launch_count(const aens_handle_t *h) nogil
+    int aens_host_alloc(long long nbytes, void **ptr) nogil
+    int aens_host_free(void *ptr) nogil
 
 STAT_NAMES = ("nsteps", "nfcns", "nerrfails", "njacs", "nlus", "nstatefcns", "nstateevents", "nstepstotal")
 SOLVER_IDS = {"ExplicitEuler": 0, "RungeKutta4": 1, "RungeKutta34": 2, "Dopri5": 3, "Radau5ODE": 4}
@@ -109,6 +112,37 @@ def nvrtc_check(src, int n, int n_p=0, int n_g=0, int n_sw=0, bint has_jac=False
     if r < 0:
         raise AensError(<int>r, err.decode(errors="replace"))
     return r
+
+
+cdef class _PinnedBlock:
+    """Owner of one cudaHostAlloc block; numpy arrays created by pinned_empty keep it alive via .base."""
+    cdef void *ptr
+    cdef long long nbytes
+
+    def __cinit__(self):
+        self.ptr = NULL
+        self.nbytes = 0
+
+    def __dealloc__(self):
+        if self.ptr != NULL:
+            aens_host_free(self.ptr)
+            self.ptr = NULL
+
+
+def pinned_empty(shape, dtype=np.float64):
+    """numpy array in page-locked host memory (needs a CUDA device)."""
+    dt = np.dtype(dtype)
+    shape = (shape,) if np.isscalar(shape) else tuple(shape)
+    cdef long long nbytes = int(np.prod(shape, dtype=np.int64)) * dt.itemsize
+    cdef _PinnedBlock blk = _PinnedBlock()
+    cdef int rc = aens_host_alloc(nbytes, &blk.ptr)
+    if rc != 0:
+        raise AensError(rc, "cudaHostAlloc(%d bytes) failed" % nbytes)
+    blk.nbytes = nbytes
+    cdef np.npy_intp n = nbytes
+    cdef np.ndarray raw = np.PyArray_SimpleNewFromData(1, &n, np.NPY_UINT8, blk.ptr)
+    np.set_array_base(raw, blk)
+    return raw.view(dt).reshape(shape)
 
 
 def measure_fp64_peak(int device=0, double seconds=1.0):
@@ -199,6 +233,9 @@ cdef class Handle:
         self.N = N
         self.n_out = 0
 
+    def reset(self):
+        self._check(aens_reset(self.h))
+
     def set_opts(self, dict d):
         cdef aens_opts_t o
         self._check(aens_default_opts(d["solver"], &o))
@@ -274,31 +311,40 @@ cdef class Handle:
         self._check(aens_last_kernel_ms(self.h, &ms))
         return ms
 
-    def get_final(self, bint want_y=True, bint want_sw=True):
-        """Returns (t[N], y[N,n] or None, sw[N,n_sw] or None, status[N])."""
-        cdef np.ndarray[double, ndim=1, mode="c"] t = np.empty(self.N, dtype=np.float64)
-        cdef np.ndarray[int, ndim=1, mode="c"] st = np.empty(self.N, dtype=np.intc)
-        cdef np.ndarray[double, ndim=2, mode="c"] y
-        cdef np.ndarray[np.uint8_t, ndim=2, mode="c"] sw
+    def get_final(self, bint want_y=True, bint want_sw=True, bint want_t=True, out_t=None, out_y=None,
+                  out_status=None):
+        """Returns (t[N] or None, y[N,n] or None, sw[N,n_sw] or None, status[N]).  out_* may be caller-owned
+        (e.g. pinned) C-contiguous arrays of the right shape/dtype that are filled instead of fresh ones."""
+        cdef np.ndarray t_arr, st_arr, y_arr, sw_arr
+        cdef double *tp = NULL
         cdef double *yp = NULL
         cdef unsigned char *sp = NULL
+        cdef int *stp = NULL
+        cdef object to = None
         cdef object yo = None
         cdef object so = None
+        if want_t:
+            t_arr = out_t if out_t is not None else np.empty(self.N, dtype=np.float64)
+            assert t_arr.dtype == np.float64 and t_arr.size == self.N and t_arr.flags.c_contiguous
+            tp = <double*>np.PyArray_DATA(t_arr)
+            to = t_arr
+        st_arr = out_status if out_status is not None else np.empty(self.N, dtype=np.intc)
+        assert st_arr.dtype == np.intc and st_arr.size == self.N and st_arr.flags.c_contiguous
+        stp = <int*>np.PyArray_DATA(st_arr)
         if want_y:
-            y = np.empty((self.N, self.n), dtype=np.float64)
-            yp = &y[0, 0]
-            yo = y
+            y_arr = out_y if out_y is not None else np.empty((self.N, self.n), dtype=np.float64)
+            assert y_arr.dtype == np.float64 and y_arr.size == self.N * self.n and y_arr.flags.c_contiguous
+            yp = <double*>np.PyArray_DATA(y_arr)
+            yo = y_arr
         if want_sw and self.n_sw:
-            sw = np.empty((self.N, self.n_sw), dtype=np.uint8)
-            sp = &sw[0, 0]
-            so = sw
-        cdef double *tp = &t[0]
-        cdef int *stp = &st[0]
+            sw_arr = np.empty((self.N, self.n_sw), dtype=np.uint8)
+            sp = <unsigned char*>np.PyArray_DATA(sw_arr)
+            so = sw_arr
         cdef int rc
         with nogil:
             rc = aens_get_final(self.h, tp, yp, sp, stp)
         self._check(rc)
-        return t, yo, so, st
+        return to, yo, so, st_arr
 
     def get_stats(self, which):
         cdef int w = STAT_NAMES.index(which) if isinstance(which, str) else which

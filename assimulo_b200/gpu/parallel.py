@@ -1,0 +1,107 @@
+"""Multi-GPU execution of one ensemble: contiguous member blocks per rank, ONE all-gather at the end.
+
+The members are independent, so the path shards with no data-path collective: rank r of G
+integrates members [r*B, min((r+1)*B, N)) with B = ceil(N/G) on its own GPU, and the final
+``{t, y, status, statistics, event counts/times}`` are exchanged once with ``all_gather`` -- over NCCL / NVLink
+directly from the library's SoA device buffers when the process group's backend is NCCL, through host tensors
+with gloo (CPU tests).  Dense-output rows stay on the producing GPU.
+
+One process per GPU (torchrun); ``torch.distributed`` is plumbing only.
+"""
+import numpy as np
+
+
+def shard_bounds(N, rank, world):
+    """[lo, hi) of this rank's contiguous block and the padded block size B = ceil(N / world)."""
+    B = -(-int(N) // int(world))
+    lo = min(rank * B, N)
+    hi = min(lo + B, N)
+    return lo, hi, B
+
+
+def cost_balanced_order(cost, world=1):
+    """Fetch order for ``solver.order``: most expensive members first (longest-processing-time rule), dealt
+    warp-wise so that every 32-lane chunk holds members of similar cost.  `cost` is any per-member proxy
+    (e.g. the stiffness parameter)."""
+    cost = np.asarray(cost)
+    return np.argsort(-cost, kind="stable").astype(np.intc)
+
+
+def shard_problem(problem, rank, world):
+    """A Batched_Explicit_Problem holding only this rank's block (padded to B by repeating its last member so
+    that all ranks gather equal-sized buffers)."""
+    from .problem import Batched_Explicit_Problem
+    lo, hi, B = shard_bounds(problem.N, rank, world)
+    if hi <= lo:  # more ranks than members: run a copy of the last member, dropped after the gather
+        lo, hi = problem.N - 1, problem.N
+    idx = np.concatenate([np.arange(lo, hi), np.full(B - (hi - lo), hi - 1, dtype=np.int64)])
+    kw = dict(y0=problem.y0[idx], p0=problem.p0[idx] if problem.n_p else None,
+              sw0=problem.sw0[idx] if problem.n_sw else None, t0=problem.t0, name=problem.name)
+    if problem.model is not None:
+        return Batched_Explicit_Problem(model=problem.model, **kw)
+    return Batched_Explicit_Problem(source=problem.source, n=problem.n, n_p=problem.n_p, n_g=problem.n_g,
+                                    n_sw=problem.n_sw, has_jac=problem.has_jac, **kw)
+
+
+class _DevView(object):
+    """Exposes a raw device buffer of the library to torch through __cuda_array_interface__ (zero copy)."""
+
+    def __init__(self, ptr, shape, typestr):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False),
+                                         "version": 2, "strides": None}
+
+
+def gather_final(solver, N_total, group=None):
+    """All-gather the final state of a sharded run.  `solver` is this rank's solver after simulate() on its
+    shard.  Returns dict(t[N], y[N,n], status[N], statistics{name:total}, nsteps[N]) on every rank."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    n = solver.problem.n
+    B = solver.N
+    backend = dist.get_backend(group)
+    h = solver._handle
+    if backend == "nccl":
+        dev = torch.device("cuda", torch.cuda.current_device())
+        solver._handle.sync()
+
+        def view(which, shape, typestr):
+            ptr, _ = h.device_ptr(which)
+            return torch.as_tensor(_DevView(ptr, shape, typestr), device=dev)
+        t_loc = view(0, (B,), "<f8")
+        y_loc = view(1, (n, B), "<f8")
+        st_loc = view(2, (B,), "<i4")
+        stats_loc = view(3, (8, B), "<i4")
+        outs = []
+        for loc in (t_loc, y_loc, st_loc, stats_loc):
+            out = torch.empty((world,) + tuple(loc.shape), dtype=loc.dtype, device=dev)
+            dist.all_gather_into_tensor(out, loc.contiguous(), group=group)
+            outs.append(out)
+        torch.cuda.synchronize()
+        t_all, y_all, st_all, stats_all = [o.cpu().numpy() for o in outs]
+    else:
+        t_loc = torch.from_numpy(np.ascontiguousarray(solver.t_members))
+        y_loc = torch.from_numpy(np.ascontiguousarray(solver.y.T))
+        st_loc = torch.from_numpy(np.ascontiguousarray(solver.status.astype(np.int32)))
+        stats_loc = torch.from_numpy(np.stack([solver.statistics.per_member(k) for k in
+                                               ("nsteps", "nfcns", "nerrfails", "njacs", "nlus", "nstatefcns",
+                                                "nstateevents", "nstepstotal")]).astype(np.int32))
+        outs = []
+        for loc in (t_loc, y_loc, st_loc, stats_loc):
+            lst = [torch.empty_like(loc) for _ in range(world)]
+            dist.all_gather(lst, loc, group=group)
+            outs.append(torch.stack(lst).numpy())
+        t_all, y_all, st_all, stats_all = outs
+    return assemble(t_all, y_all, st_all, stats_all, N_total)
+
+
+def assemble(t_all, y_all, st_all, stats_all, N_total):
+    """[world, ...] per-rank blocks (SoA) -> member-major arrays of the first N_total members."""
+    world, n, B = y_all.shape
+    t = t_all.reshape(world * B)[:N_total]
+    y = np.transpose(y_all, (0, 2, 1)).reshape(world * B, n)[:N_total]
+    status = st_all.reshape(world * B)[:N_total]
+    stats = np.transpose(stats_all, (1, 0, 2)).reshape(stats_all.shape[1], world * B)[:, :N_total]
+    names = ("nsteps", "nfcns", "nerrfails", "njacs", "nlus", "nstatefcns", "nstateevents", "nstepstotal")
+    return {"t": t, "y": y, "status": status, "stats_per_member": {k: stats[i] for i, k in enumerate(names)},
+            "statistics": {k: int(stats[i].astype(np.int64).sum()) for i, k in enumerate(names)}}

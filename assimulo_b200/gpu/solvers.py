@@ -60,7 +60,7 @@ class Batched_Explicit_ODE(object):
             raise Explicit_ODE_Exception("The problem needs to be a subclass of a Batched_Explicit_Problem.")
         self.problem = problem
         self.options = {"arith": "fast", "refill_threshold": 32, "order": None, "event_slots": 16,
-                        "verbosity": 30, "store_event_points": True}
+                        "verbosity": 30, "store_event_points": True, "reuse_buffers": False}
         self.supports = {"state_events": False, "interpolated_output": False, "report_continuously": False}
         self.problem_info = {"dim": problem.n, "dimRoot": problem.n_g, "state_events": problem.n_g > 0,
                              "jac_fcn": problem.has_jac, "switches": problem.n_sw > 0}
@@ -125,10 +125,11 @@ class Batched_Explicit_ODE(object):
         if y0.shape[-1] != self._leny:
             raise Explicit_ODE_Exception("y0 must be of the same length as the original problem.")
         self.t = float(t0)
-        self.y = np.ascontiguousarray(np.broadcast_to(y0.reshape(-1, self._leny), (self.N, self._leny))).copy()
+        # no defensive copies of ensemble-sized arrays: they are only read when uploaded to the device
+        self.y = np.ascontiguousarray(np.broadcast_to(y0.reshape(-1, self._leny), (self.N, self._leny)))
         if sw0 is not None:
             self.sw = np.ascontiguousarray(np.broadcast_to(np.asarray(sw0, dtype=bool).reshape(-1, self.problem.n_sw),
-                                                           (self.N, self.problem.n_sw))).copy()
+                                                           (self.N, self.problem.n_sw)))
         self.t_members = np.full(self.N, self.t)
         self._dirty = True
 
@@ -177,11 +178,20 @@ class Batched_Explicit_ODE(object):
         h.set_opts(self._opts_dict())
         h.set_output(output_list, int(self.options["event_slots"]))
         h.set_schedule(int(self.options["refill_threshold"]), self.options["order"])
-        self.problem.handle_result(self, t0, self.y.copy())
+        self.problem.handle_result(self, t0, self.y)
         h.simulate(tfinal)
         self._launched = True
         self.elapsed_kernel_ms = h.last_kernel_ms()
-        tm, y, sw, status = h.get_final()
+        if self.options["reuse_buffers"]:
+            # page-locked result buffers allocated once and overwritten by every simulate() call: rows returned
+            # by an earlier call alias them (documented trade: no ensemble-sized allocation or copy per call)
+            if getattr(self, "_pin", None) is None or self._pin[0].shape[0] != self.N:
+                c = _core()
+                self._pin = (c.pinned_empty((self.N,), np.float64), c.pinned_empty((self.N, self._leny), np.float64),
+                             c.pinned_empty((self.N,), np.intc))
+            tm, y, sw, status = h.get_final(out_t=self._pin[0], out_y=self._pin[1], out_status=self._pin[2])
+        else:
+            tm, y, sw, status = h.get_final()
         self.t_members, self.y, self.status = tm, y, status
         if sw is not None:
             self.sw = sw.astype(bool)
@@ -193,13 +203,15 @@ class Batched_Explicit_ODE(object):
             for k, tk in enumerate(output_list):
                 self.problem.handle_result(self, float(tk), dense[k])
         else:
-            self.problem.handle_result(self, tfinal, self.y.copy())
+            self.problem.handle_result(self, tfinal, self.y)
         # the ensemble's current time: members that failed or were terminated stopped early (see status)
-        self.t = tfinal if np.all(self.status == ST_COMPLETE) else float(np.min(self.t_members))
+        self.t = tfinal if not self.status.any() else float(np.min(self.t_members))
         if self.problem.n_g > 0:
             self._events = h.get_events()
         self.finalize()
         self.problem.finalize(self)
+        if self.options["reuse_buffers"]:
+            return self.t_sol, self.y_sol  # list of [N, n] rows, no ensemble-sized stacking copy
         return self.t_sol, np.array(self.y_sol)
 
     __call__ = simulate
@@ -329,6 +341,7 @@ class ExplicitEuler(_FixedStep):
     def __init__(self, problem, **kw):
         Batched_Explicit_ODE.__init__(self, problem, **kw)
         self.options["h"] = 0.01
+        self.options["arith"] = "strict"  # fixed-step parity bar is <=1e-13: reference operation order, no FMA
         self.supports.update(report_continuously=True, interpolated_output=True, state_events=True)
 
 
@@ -339,6 +352,7 @@ class RungeKutta4(_FixedStep):
     def __init__(self, problem, **kw):
         Batched_Explicit_ODE.__init__(self, problem, **kw)
         self.options["h"] = 0.01
+        self.options["arith"] = "strict"  # see ExplicitEuler
 
 
 class RungeKutta34(Batched_Explicit_ODE):

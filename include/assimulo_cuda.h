@@ -125,6 +125,9 @@ int aens_model_dims(const aens_handle_t *h, int *n, int *n_p, int *n_g, int *n_s
  * Resets every member to (t0, y0, sw0) and clears statistics and event logs. */
 int aens_set_ensemble(aens_handle_t *h, long long N, const double *y0, const double *p,
                       const unsigned char *sw0, double t0);
+/* Back to (t0, y0, sw0) of the last aens_set_ensemble, device to device, asynchronous on the handle's stream
+ * (Explicit_ODE.reset(), src/explicit_ode.pyx:98-106). */
+int aens_reset(aens_handle_t *h);
 int aens_set_opts(aens_handle_t *h, const aens_opts_t *o);
 
 /* Output: n_out grid times shared by all members (ODE.simulate's output_list, src/ode.pyx:273-287);
@@ -164,6 +167,11 @@ int aens_get_events(aens_handle_t *h, int *count, double *t_ev, int *info);
 int aens_device_ptr(aens_handle_t *h, int which, void **ptr, long long *bytes);
 /* CUDA stream of the handle (cudaStream_t as void*) */
 int aens_stream(aens_handle_t *h, void **stream);
+
+/* Page-locked host memory for the caller's arrays: host<->device copies of pinned buffers run at full PCIe rate
+ * and asynchronously (the reference has no analogue; its arrays never leave the host). */
+int aens_host_alloc(long long bytes, void **ptr);
+int aens_host_free(void *ptr);
 
 /* Measurement helpers (not on the product path): sustained fp64 FMA throughput of the device measured with a
  * dependent-chain DFMA kernel for ~`seconds`; result in TFLOP/s (2 flops per DFMA). */

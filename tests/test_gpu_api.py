@@ -1,0 +1,252 @@
+"""-m gpu: the reference-facing surface on the device -- solver classes (simulate / ncp / continuation / statistics /
+event log), NVRTC-compiled user models, the raw C ABI through ctypes, and full-size property checks."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import cases
+import ens_oracle as O
+from conftest import ROOT, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def test_simulate_surface_dopri5():
+    from assimulo_b200.gpu import Batched_Explicit_Problem, Dopri5
+    N = 1000
+    y0, mu = cases.vdp_sweep(N)
+    sim = Dopri5(Batched_Explicit_Problem(model="vdp", y0=y0, p0=mu, name="vdp sweep"))
+    sim.rtol, sim.atol = 1e-6, 1e-6
+    t, y = sim.simulate(2.0)
+    assert t == [0.0, 2.0] and y.shape == (2, N, 2)
+    assert np.array_equal(y[0], y0)
+    o = O.simulate("vdp", "Dopri5", y0, mu, tf=2.0, rtol=1e-6, atol=1e-6)
+    assert rel_err(y[-1], o["y"]) <= 1e-5
+    assert abs(sim.statistics["nsteps"] - o["stats"]["nsteps"].sum()) <= 0.02 * o["stats"]["nsteps"].sum()
+    assert sim.statistics["nfcns"] == o["stats"]["nfcns"].sum() or abs(
+        sim.statistics["nfcns"] - o["stats"]["nfcns"].sum()) <= 0.02 * o["stats"]["nfcns"].sum()
+    assert sim.statistics.per_member("nsteps").shape == (N,)
+    assert sim.t == 2.0 and (sim.status == 0).all() and sim.elapsed_kernel_ms > 0
+    sim.print_statistics()
+
+
+def test_ncp_output_grid_and_continuation():
+    """ODE.simulate: rows at linspace(t0, tf, ncp+1)[1:]; a second simulate() continues from the current time
+    (src/ode.pyx:195-196,222, examples/euler_basic.py:49-50) and must land on the one-shot result."""
+    from assimulo_b200.gpu import Batched_Explicit_Problem, Dopri5, ExplicitEuler
+    N = 257
+    y0, mu = cases.vdp_sweep(N)
+    sim = Dopri5(Batched_Explicit_Problem(model="vdp", y0=y0, p0=mu))
+    sim.arith = "strict"
+    t, y = sim.simulate(2.0, 20)
+    assert len(t) == 21 and np.allclose(t, np.linspace(0, 2, 21)) and y.shape == (21, N, 2)
+    grid = np.linspace(0, 2, 21)[1:]
+    o = O.simulate("vdp", "Dopri5", y0, mu, tf=2.0, t_grid=grid)
+    assert np.nanmax(np.abs(np.transpose(y[1:], (1, 0, 2)) - o["dense"])) <= 1e-9
+    # continuation 0 -> 1 -> 2 with a fixed-step solver equals 0 -> 2 exactly when 1.0 is on the step grid
+    a = ExplicitEuler(Batched_Explicit_Problem(model="linear", y0=[[4.0]] * 8, p0=[-1.0, 0.0, 0.0]))
+    a.h = 0.01
+    a.simulate(3.0)
+    a.simulate(5.0)
+    assert a.t == 5.0
+    assert abs(a.y[0, 0] - 0.02628193) < 1e-6                      # examples/euler_basic.py:63
+    # ncp_list
+    t, y = sim.simulate(3.0, ncp_list=[2.5, 2.75])
+    assert t == [2.0, 2.5, 2.75, 3.0]
+    # reset
+    sim.reset()
+    t, y = sim.simulate(2.0)
+    assert rel_err(y[-1], o["y"]) <= 1e-9
+
+
+def test_rk4_ignores_ncp_like_the_reference():
+    from assimulo_b200.gpu import Batched_Explicit_Problem, RungeKutta4
+    sim = RungeKutta4(Batched_Explicit_Problem(model="linear", y0=[[4.0]], p0=[-1.0, 0.0, 0.0]))
+    t, y = sim.simulate(5.0, 100)
+    assert t == [0.0, 5.0] and abs(y[-1][0, 0] - 0.02695179) < 1e-6
+
+
+def test_event_log_and_switches_through_the_solver_class():
+    from assimulo_b200.gpu import Batched_Explicit_Problem, Dopri5, Radau5ODE
+    N = 64
+    y0, p, sw0 = cases.ball_sweep(N)
+    o = O.simulate("ball", "Dopri5", y0, p, sw0, tf=3.0, max_ev=16)
+    sim = Dopri5(Batched_Explicit_Problem(model="ball", y0=y0, p0=p, sw0=sw0))
+    sim.simulate(3.0)
+    cnt, te, info = sim.event_log
+    assert np.array_equal(cnt, o["stats"]["nstateevents"]) and sim.statistics["nstateevents"] == cnt.sum()
+    for m in (0, N // 2, N - 1):
+        ev = sim.event_times(m)
+        assert len(ev) == cnt[m] and np.all(np.diff(ev) > 0)
+        assert np.max(np.abs(ev - o["ev_t"][m, :cnt[m]])) < 1e-9
+    assert np.array_equal(sim.sw.astype(np.uint8), o["sw"])
+    # ring semantics: only the last `event_slots` events are kept, in slot e % slots
+    sim2 = Dopri5(Batched_Explicit_Problem(model="ball", y0=y0, p0=p, sw0=sw0))
+    sim2.event_slots = 4
+    sim2.simulate(3.0)
+    for m in (0, N - 1):
+        assert np.allclose(sim2.event_times(m), o["ev_t"][m, cnt[m] - 4:cnt[m]], atol=1e-9)
+    r = Radau5ODE(Batched_Explicit_Problem(model="extended", y0=[0.0, -1.0, 0.0]))
+    r.simulate(10.0)
+    np.testing.assert_allclose(r.y[0], [8.0, 3.0, 2.0], atol=1e-6)      # test_radau5.py:341-354
+    assert r.statistics["nstateevents"] == 1
+
+
+VDP_SRC = r"""
+__device__ void aens_rhs(double t, const double* y, const unsigned char* sw, const double* p, double* yd) {
+    yd[0] = y[1];
+    yd[1] = p[0] * ((1. - y[0] * y[0]) * y[1] - y[0]);
+}
+__device__ void aens_jac(double t, const double* y, const unsigned char* sw, const double* p, double* J) {
+    J[0] = 0.; J[1] = p[0] * (-2. * y[0] * y[1] - 1.); J[2] = 1.; J[3] = p[0] * (1. - y[0] * y[0]);
+}
+"""
+BALL_SRC = r"""
+__device__ void aens_rhs(double t, const double* y, const unsigned char* sw, const double* p, double* yd) {
+    yd[0] = y[1]; yd[1] = p[0];
+}
+__device__ void aens_events(double t, const double* y, const unsigned char* sw, const double* p, double* g) {
+    g[0] = sw[0] ? y[0] : 5.; g[1] = sw[1] ? y[1] : 5.;
+}
+__device__ int aens_handle_event(double t, double* y, unsigned char* sw, const int* info, const double* p) {
+    if (info[0] != 0) { sw[0] = 0; sw[1] = 1; y[1] = -p[1] * y[1]; } else { sw[0] = 1; sw[1] = 0; }
+    return 0;
+}
+"""
+TERMINATE_SRC = r"""
+__device__ void aens_rhs(double t, const double* y, const unsigned char* sw, const double* p, double* yd) { yd[0] = 1.0; }
+__device__ void aens_events(double t, const double* y, const unsigned char* sw, const double* p, double* g) { g[0] = y[0] - p[0]; }
+__device__ int aens_handle_event(double t, double* y, unsigned char* sw, const int* info, const double* p) { return 1; }
+"""
+
+
+def test_nvrtc_user_model_equals_builtin():
+    """A model supplied as a CUDA source string runs through the same kernel templates: identical results."""
+    from assimulo_b200.gpu import Batched_Explicit_Problem, Dopri5, Radau5ODE, RungeKutta4
+    N = 512
+    y0, mu = cases.vdp_sweep(N)
+    for cls, kw in ((Dopri5, {}), (RungeKutta4, {"h": 1e-3}), (Radau5ODE, {})):
+        res = []
+        for prob in (Batched_Explicit_Problem(model="vdp", y0=y0, p0=mu),
+                     Batched_Explicit_Problem(source=VDP_SRC, n=2, n_p=1, has_jac=True, y0=y0, p0=mu)):
+            sim = cls(prob)
+            sim.arith = "strict"
+            for k, v in kw.items():
+                setattr(sim, k, v)
+            sim.simulate(2.0)
+            res.append((sim.y.copy(), sim.statistics["nsteps"]))
+        assert np.array_equal(res[0][0], res[1][0]) and res[0][1] == res[1][1], cls.__name__
+    y0, p, sw0 = cases.ball_sweep(128)
+    a = Dopri5(Batched_Explicit_Problem(model="ball", y0=y0, p0=p, sw0=sw0))
+    b = Dopri5(Batched_Explicit_Problem(source=BALL_SRC, n=2, n_p=2, n_g=2, n_sw=2, y0=y0, p0=p, sw0=sw0))
+    for s in (a, b):
+        s.arith = "strict"          # fast arithmetic too: the second cubin is compiled on demand
+        s.simulate(3.0)
+    assert np.array_equal(a.y, b.y) and np.array_equal(a.event_log[1], b.event_log[1])
+    b.arith = "fast"
+    b.reset()
+    b.simulate(3.0)
+    assert rel_err(b.y, a.y) < 1e-5
+
+
+def test_handle_event_can_terminate_a_member():
+    """TerminateSimulation from handle_event (src/explicit_ode.pyx:260-262) -> per-member status 1."""
+    from assimulo_b200.gpu import Batched_Explicit_Problem, Dopri5
+    thr = np.array([[0.5], [5.0]])
+    sim = Dopri5(Batched_Explicit_Problem(source=TERMINATE_SRC, n=1, n_p=1, n_g=1, n_sw=1, y0=[[0.0], [0.0]],
+                                          p0=thr, sw0=[[1], [1]]))
+    sim.simulate(2.0)
+    assert sim.status.tolist() == [1, 0]
+    assert abs(sim.t_members[0] - 0.5) < 1e-9 and sim.t_members[1] == 2.0
+    assert abs(sim.y[0, 0] - 0.5) < 1e-9 and abs(sim.y[1, 0] - 2.0) < 1e-9
+
+
+def test_bad_source_raises_with_compiler_log():
+    from assimulo_b200.gpu import Batched_Explicit_Problem, Dopri5, _core
+    sim = Dopri5(Batched_Explicit_Problem(source="__device__ void aens_rhs(int x) { nope }", n=1, y0=[[0.0]]))
+    with pytest.raises(_core.AensError) as e:
+        sim.simulate(1.0)
+    assert e.value.code == -3 and "error" in str(e.value)
+
+
+def test_raw_c_abi_through_ctypes():
+    """The boundary is a plain C ABI: drive it with ctypes only (no Cython, no torch)."""
+    lib = C.CDLL(os.path.join(ROOT, "assimulo_b200", "lib", "libassimulo_cuda.so"))
+
+    class Opts(C.Structure):
+        _fields_ = [("solver", C.c_int), ("arith", C.c_int), ("maxsteps", C.c_int), ("newt", C.c_int),
+                    ("usejac", C.c_int), ("reserved", C.c_int), ("rtol", C.c_double), ("atol", C.c_double * 16),
+                    ("h", C.c_double), ("inith", C.c_double), ("maxh", C.c_double), ("safe", C.c_double),
+                    ("fac1", C.c_double), ("fac2", C.c_double), ("beta", C.c_double), ("thet", C.c_double),
+                    ("fnewt", C.c_double), ("quot1", C.c_double), ("quot2", C.c_double)]
+    lib.aens_last_error.restype = C.c_char_p
+    lib.aens_simulate.argtypes = [C.c_void_p, C.c_double]
+    lib.aens_set_ensemble.argtypes = [C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double]
+    h = C.c_void_p()
+    assert lib.aens_create(0, C.byref(h)) == 0
+    assert lib.aens_simulate(h, 1.0) == -4 and b"model" in lib.aens_last_error(h)      # call order enforced
+    assert lib.aens_set_model_builtin(h, b"no_such_model") == -1
+    assert lib.aens_set_model_builtin(h, b"vdp") == 0
+    N = 777
+    y0, mu = cases.vdp_sweep(N)
+    y0 = np.ascontiguousarray(y0)
+    mu = np.ascontiguousarray(mu)
+    assert lib.aens_set_ensemble(h, N, y0.ctypes.data, mu.ctypes.data, None, 0.0) == 0
+    o = Opts()
+    assert lib.aens_default_opts(3, C.byref(o)) == 0
+    o.arith = 0
+    assert lib.aens_set_opts(h, C.byref(o)) == 0
+    assert lib.aens_set_output(h, 0, None, 0) == 0
+    assert lib.aens_simulate(h, 2.0) == 0
+    t = np.empty(N)
+    y = np.empty((N, 2))
+    st = np.empty(N, dtype=np.int32)
+    ns = np.empty(N, dtype=np.int32)
+    assert lib.aens_get_final(h, t.ctypes.data_as(C.c_void_p), y.ctypes.data_as(C.c_void_p), None,
+                              st.ctypes.data_as(C.c_void_p)) == 0
+    assert lib.aens_get_stats(h, 0, ns.ctypes.data_as(C.c_void_p)) == 0
+    ref = O.simulate("vdp", "Dopri5", y0, mu, tf=2.0)
+    assert np.array_equal(ns, ref["stats"]["nsteps"]) and rel_err(y, ref["y"]) < 1e-10 and (st == 0).all()
+    sums = (C.c_longlong * 8)()
+    assert lib.aens_get_stats_sum(h, sums) == 0 and sums[0] == ns.sum()
+    assert lib.aens_reset(h) == 0 and lib.aens_simulate(h, 2.0) == 0
+    y2 = np.empty((N, 2))
+    lib.aens_get_final(h, None, y2.ctypes.data_as(C.c_void_p), None, None)
+    assert np.array_equal(y, y2)                                                      # reset + rerun is deterministic
+    assert lib.aens_destroy(C.byref(h)) == 0 and not h.value
+
+
+def test_full_size_properties_cfg2():
+    """BASELINE cfg 2 at full size (2^20 members): size-independent properties + a strided oracle sample."""
+    from assimulo_b200.gpu import Batched_Explicit_Problem, Dopri5, RungeKutta4, RungeKutta34
+    N = 1 << 20
+    y0, mu = cases.vdp_sweep(N)
+    idx = np.arange(0, N, 4096)
+    for cls, oname, kw in ((RungeKutta4, "RungeKutta4", dict(h=1e-3)),
+                           (RungeKutta34, "RungeKutta34", dict(rtol=1e-6, atol=1e-6, inith=0.01)),
+                           (Dopri5, "Dopri5", dict(rtol=1e-6, atol=1e-6))):
+        sim = cls(Batched_Explicit_Problem(model="vdp", y0=y0, p0=mu))
+        for k, v in kw.items():
+            setattr(sim, k, v)
+        sim.options["reuse_buffers"] = True
+        sim.simulate(2.0)
+        assert not sim.status.any() and np.isfinite(sim.y).all() and (sim.t_members == 2.0).all()
+        ns = sim.statistics.per_member("nsteps")
+        assert sim.statistics["nsteps"] == ns.astype(np.int64).sum()
+        if oname == "RungeKutta4":
+            assert (ns == 2001).all()
+        else:
+            assert np.abs(np.diff(ns.astype(int))).max() <= 3       # smooth sweep: neighbours cost the same
+        o = O.simulate("vdp", oname, y0[idx], mu[idx], tf=2.0, **kw)
+        tol = 1e-13 if oname == "RungeKutta4" else 1e-5
+        assert rel_err(sim.y[idx], o["y"]) <= tol
+        assert abs(int(ns[idx].sum()) - int(o["stats"]["nsteps"].sum())) <= 0.02 * o["stats"]["nsteps"].sum()
+        # the members are independent: a permuted ensemble gives the permuted result
+        perm = np.random.RandomState(0).permutation(N)[:65536]
+        sub = cls(Batched_Explicit_Problem(model="vdp", y0=y0[perm], p0=mu[perm]))
+        for k, v in kw.items():
+            setattr(sub, k, v)
+        sub.simulate(2.0)
+        assert rel_err(sub.y, sim.y[perm]) <= (0 if oname == "RungeKutta4" else 1e-12)

@@ -1,0 +1,126 @@
+"""Host-side mirror of the reference's solver surface (no GPU): option names, defaults, validation messages
+(src/solvers/runge_kutta.py:209-428, src/lib/radau_core.py:29-434), problem broadcasting, output-grid rules
+(src/ode.pyx:273-287) and the sharding helpers."""
+import numpy as np
+import pytest
+
+from assimulo_b200.gpu import (AssimuloException, Batched_Explicit_Problem, Dopri5, Dopri5_Exception, ExplicitEuler,
+                               Explicit_ODE_Exception, Radau5ODE, Radau_Exception, RungeKutta4, RungeKutta34,
+                               parallel)
+
+
+def vdp(N=4):
+    return Batched_Explicit_Problem(model="vdp", y0=[2.0, -0.6], p0=np.linspace(1, 2, N)[:, None])
+
+
+def test_problem_broadcasting_and_defaults():
+    p = vdp(5)
+    assert p.N == 5 and p.y0.shape == (5, 2) and p.p0.shape == (5, 1) and p.sw0.shape == (5, 0)
+    b = Batched_Explicit_Problem(model="ball", y0=np.array([[1.0, 0.0], [2.0, 0.0]]))
+    assert b.N == 2 and b.p0.tolist() == [[-9.81, 0.88]] * 2 and b.sw0.tolist() == [[1, 0]] * 2
+    with pytest.raises(AssimuloException):
+        Batched_Explicit_Problem(model="nope", y0=[1.0])
+    with pytest.raises(AssimuloException):
+        Batched_Explicit_Problem(y0=[1.0])
+    s = Batched_Explicit_Problem(source="...", n=2, n_p=1, y0=[[0.0, 1.0]] * 3, p0=[[1.0]] * 3)
+    assert s.N == 3 and s.model is None
+
+
+def test_defaults_match_the_reference():
+    d = Dopri5(vdp())
+    assert (d.safe, d.fac1, d.fac2, d.beta, d.inith, d.rtol, d.maxsteps) == (0.9, 0.2, 10.0, 0.04, 0.0, 1e-6, 100000)
+    assert d.maxh == np.inf and d.atol.tolist() == [1e-6, 1e-6] and d.arith == "fast"
+    r = RungeKutta34(vdp())
+    assert (r.inith, r.rtol, r.maxsteps) == (0.01, 1e-6, 10000)
+    assert RungeKutta4(vdp()).h == 0.01 and ExplicitEuler(vdp()).h == 0.01
+    assert RungeKutta4(vdp()).arith == "strict" and ExplicitEuler(vdp()).arith == "strict"
+    ra = Radau5ODE(vdp())
+    assert (ra.inith, ra.newt, ra.thet, ra.quot1, ra.quot2, ra.fac1, ra.fac2, ra.safe) == \
+        (0.01, 7, 1e-3, 1.0, 1.2, 0.2, 8.0, 0.9)
+    assert ra.usejac is True and ra.fnewt is None and ra.maxh is None and ra.linear_solver == "DENSE"
+    assert Radau5ODE(Batched_Explicit_Problem(model="gyro", y0=np.zeros(12))).usejac is False
+    for s in (d, r, ra, ExplicitEuler(vdp())):
+        assert s.supports["state_events"] and s.supports["interpolated_output"]
+    assert not RungeKutta4(vdp()).supports["interpolated_output"]
+
+
+def test_option_validation_messages():
+    d = Dopri5(vdp())
+    with pytest.raises(Dopri5_Exception, match="Relative tolerance must be a positive"):
+        d.rtol = -1.0
+    with pytest.raises(Dopri5_Exception, match="Relative tolerance must be a \\(scalar\\) float"):
+        d.rtol = "x"
+    with pytest.raises(Dopri5_Exception, match="atol must be of length one or same as the dimension"):
+        d.atol = [1e-6, 1e-6, 1e-6]
+    d.atol = 1e-4
+    assert d.atol.tolist() == [1e-4, 1e-4]
+    with pytest.raises(Dopri5_Exception, match="Maximum number of steps must be a positive integer"):
+        d.maxsteps = "many"
+    with pytest.raises(Dopri5_Exception, match="fac1 must be an integer or float"):
+        d.fac1 = "a"
+    r = RungeKutta34(vdp())
+    with pytest.raises(Explicit_ODE_Exception):
+        r.atol = -1.0
+    with pytest.raises(Explicit_ODE_Exception):
+        r.rtol = -1.0
+    ra = Radau5ODE(vdp())
+    with pytest.raises(Radau_Exception, match="'newt' must be an integer or float"):
+        ra.newt = "x"
+    with pytest.raises(Radau_Exception, match="Maximal stepsize must be a positiv"):
+        ra.maxh = -1.0
+    with pytest.raises(Radau_Exception):
+        ra.linear_solver = "SPARSE"
+    with pytest.raises(Radau_Exception):
+        Radau5ODE(Batched_Explicit_Problem(model="ball", y0=[1.0, 0.0])).usejac = True
+    with pytest.raises(AssimuloException):
+        RungeKutta4(vdp()).h = "x"
+    with pytest.raises(AssimuloException):
+        d.arith = "sloppy"
+    with pytest.raises(AssimuloException):
+        d.refill_threshold = 0
+    with pytest.raises(Explicit_ODE_Exception):
+        Dopri5(object())
+
+
+def test_simulate_argument_checks_happen_before_the_device_is_touched():
+    d = Dopri5(vdp())
+    with pytest.raises(AssimuloException, match="Final time must be"):
+        d.simulate("soon")
+    d.t = 3.0
+    with pytest.raises(AssimuloException, match="must be greater than start time"):
+        d.simulate(2.0)
+    d.t = 0.0
+    with pytest.raises(AssimuloException, match="communication points must be an integer"):
+        d.simulate(2.0, 1.5)
+
+
+def test_opts_dict_packing():
+    d = Dopri5(vdp())
+    o = d._opts_dict()
+    assert o["solver"] == 3 and o["arith"] == 1 and "maxh" not in o and o["atol"].tolist() == [1e-6, 1e-6]
+    d.maxh = 0.1
+    assert d._opts_dict()["maxh"] == 0.1
+    ra = Radau5ODE(vdp())
+    o = ra._opts_dict()
+    assert o["usejac"] == 1 and "fnewt" not in o and "maxh" not in o and o["newt"] == 7
+
+
+def test_shard_bounds_and_assemble():
+    assert parallel.shard_bounds(10, 0, 4) == (0, 3, 3)
+    assert parallel.shard_bounds(10, 3, 4) == (9, 10, 3)
+    assert parallel.shard_bounds(2, 3, 4)[0:2] == (2, 2)
+    world, n, B, N = 4, 2, 3, 10
+    y_true = np.arange(world * B * n, dtype=float).reshape(world * B, n)
+    y_all = np.stack([y_true[r * B:(r + 1) * B].T for r in range(world)])
+    t_all = np.arange(world * B, dtype=float).reshape(world, B)
+    st_all = np.zeros((world, B), dtype=np.int32)
+    stats_all = np.ones((world, 8, B), dtype=np.int32)
+    out = parallel.assemble(t_all, y_all, st_all, stats_all, N)
+    assert np.array_equal(out["y"], y_true[:N]) and np.array_equal(out["t"], np.arange(N))
+    assert out["statistics"]["nsteps"] == N
+    p = Batched_Explicit_Problem(model="vdp", y0=[2.0, -0.6], p0=np.arange(10.0)[:, None])
+    parts = [parallel.shard_problem(p, r, 4) for r in range(4)]
+    assert [q.N for q in parts] == [3, 3, 3, 3]
+    assert parts[3].p0[:, 0].tolist() == [9.0, 9.0, 9.0]          # padded with copies of the last member
+    order = parallel.cost_balanced_order([1.0, 5.0, 3.0])
+    assert order.tolist() == [1, 2, 0]

@@ -1,0 +1,75 @@
+"""N>1 path on CPU: world_size=2 `gloo` process group.  Each rank takes its contiguous block of the ensemble
+(parallel.shard_problem), "integrates" it -- here with the C oracle standing in for the device, which is exactly
+what the oracle is for -- and the single end-of-run all_gather (parallel.gather_final) must reassemble the
+whole-ensemble result on every rank."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+WORLD = 2
+N = 37  # deliberately not divisible by WORLD: the last block is padded and trimmed after the gather
+
+
+class _OracleBackedSolver(object):
+    """Quacks like a Batched_Explicit_ODE after simulate() for gather_final's host (gloo) path."""
+
+    def __init__(self, problem):
+        import ens_oracle as O
+        out = O.simulate("vdp", "Dopri5", problem.y0, problem.p0, tf=2.0, rtol=1e-6, atol=1e-6)
+        self.problem, self.N = problem, problem.N
+        self.t_members, self.y, self.status = out["t"], out["y"], out["status"]
+        self._stats = out["stats"]
+        self._handle = None
+        outer = self
+
+        class _S(dict):
+            def per_member(self, k):
+                return outer._stats[k]
+        self.statistics = _S()
+
+
+def _worker(rank, port, q):
+    for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests", "golden")):
+        sys.path.insert(0, p)
+    import torch.distributed as dist
+    import cases
+    from assimulo_b200.gpu import Batched_Explicit_Problem, parallel
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=WORLD)
+    y0, mu = cases.vdp_sweep(N)
+    full = Batched_Explicit_Problem(model="vdp", y0=y0, p0=mu)
+    shard = parallel.shard_problem(full, rank, WORLD)
+    lo, hi, B = parallel.shard_bounds(N, rank, WORLD)
+    assert shard.N == B and np.array_equal(shard.p0[: hi - lo, 0], mu[lo:hi, 0])
+    g = parallel.gather_final(_OracleBackedSolver(shard), N)
+    q.put((rank, g["y"], g["t"], g["status"], g["statistics"]["nsteps"], g["stats_per_member"]["nsteps"]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_gather_matches_single_process():
+    import torch.multiprocessing as mp
+    import cases
+    import ens_oracle as O
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29600 + os.getpid() % 300
+    procs = [ctx.Process(target=_worker, args=(r, port, q)) for r in range(WORLD)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=180) for _ in range(WORLD)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    y0, mu = cases.vdp_sweep(N)
+    ref = O.simulate("vdp", "Dopri5", y0, mu, tf=2.0, rtol=1e-6, atol=1e-6)
+    for rank, y, t, st, nsteps, per in res:
+        assert y.shape == (N, 2)
+        assert np.array_equal(y, ref["y"]) and np.array_equal(t, ref["t"])
+        assert np.array_equal(per, ref["stats"]["nsteps"]) and nsteps == int(ref["stats"]["nsteps"].sum())
+        assert (st == 0).all()
