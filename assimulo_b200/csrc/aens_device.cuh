@@ -219,9 +219,13 @@ AENS_DEV int aens_post_step(S &s, Lane<M> &L, const aens_args_t &a, long long id
         for (int i = 0; i < M::N; ++i) ye[i] = L.y[i];
         flag = aens_locate<M, S>(s, L, told, te, ye);
         if (flag == AENS_R_EVENT) {
-            tnew = te;
+            /* grid rows up to the event time come from the interpolant of the FULL step, which for the
+             * one-step methods reads L.y as its right end point: emit before L.y becomes the event state */
+            if (S::HAS_DENSE) aens_emit_grid<M, S>(s, L, a, idx, te);
 #pragma unroll
             for (int i = 0; i < M::N; ++i) L.y[i] = ye[i];
+            L.t = te;
+            return flag;
         }
     }
     if (S::HAS_DENSE) aens_emit_grid<M, S>(s, L, a, idx, tnew);

@@ -87,7 +87,7 @@ def test_event_log_and_switches_through_the_solver_class():
     sim2.event_slots = 4
     sim2.simulate(3.0)
     for m in (0, N - 1):
-        assert np.allclose(sim2.event_times(m), o["ev_t"][m, cnt[m] - 4:cnt[m]], atol=1e-9)
+        assert np.allclose(sim2.event_times(m), o["ev_t"][m, max(0, cnt[m] - 4):cnt[m]], atol=1e-9)
     r = Radau5ODE(Batched_Explicit_Problem(model="extended", y0=[0.0, -1.0, 0.0]))
     r.simulate(10.0)
     np.testing.assert_allclose(r.y[0], [8.0, 3.0, 2.0], atol=1e-6)      # test_radau5.py:341-354
