@@ -50,16 +50,16 @@ AENS_DEV double dmin(double a, double b) { return a <= b ? a : b; }
 
 #if !AENS_STRICT
 /* fp32 MUFU power for step-size heuristics only: x^e = ex2(e * lg2(x)).  x=0 -> 0, x=inf -> inf (e>0). */
-AENS_DEV float fpow(float x, float e) { return exp2f(e * __log2f(x)); }
-/* reciprocal of a strictly positive, normal fp64 number: MUFU.RCP64H seed + 2 Newton steps (~1 ulp) */
+AENS_DEV float flg2(float x) { float r; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+AENS_DEV float fex2(float x) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+AENS_DEV float fpow(float x, float e) { return fex2(e * flg2(x)); }
+/* reciprocal of a strictly positive, normal fp64 number for the error norms: MUFU.RCP64H seed (~2^-23) + one
+ * Newton step -> ~2^-46 relative, far below what an accept/reject decision can see */
 AENS_DEV double rcp_pos(double b) {
     double r;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b));
-    double e = fma(-b, r, 1.0);
-    r = fma(r, e, r);
-    e = fma(-b, r, 1.0);
-    r = fma(r, e, r);
-    return r;
+    const double e = fma(-b, r, 1.0);
+    return fma(r, e, r);
 }
 #endif
 
@@ -447,17 +447,23 @@ struct RK34 {
 /* Dopri5: DOPCOR dopri5.f:356-556, HINIT :558-619, CONTD5 :621-644, CDOPRI :646-692                         */
 /* ------------------------------------------------------------------------------------------------------- */
 namespace dp {
-constexpr double c2 = 0.2, c3 = 0.3, c4 = 0.8, c5 = 8.0 / 9.0;
-constexpr double a21 = 0.2, a31 = 3.0 / 40.0, a32 = 9.0 / 40.0, a41 = 44.0 / 45.0, a42 = -56.0 / 15.0,
-                 a43 = 32.0 / 9.0, a51 = 19372.0 / 6561.0, a52 = -25360.0 / 2187.0, a53 = 64448.0 / 6561.0,
-                 a54 = -212.0 / 729.0, a61 = 9017.0 / 3168.0, a62 = -355.0 / 33.0, a63 = 46732.0 / 5247.0,
-                 a64 = 49.0 / 176.0, a65 = -5103.0 / 18656.0, a71 = 35.0 / 384.0, a73 = 500.0 / 1113.0,
-                 a74 = 125.0 / 192.0, a75 = -2187.0 / 6784.0, a76 = 11.0 / 84.0;
-constexpr double e1 = 71.0 / 57600.0, e3 = -71.0 / 16695.0, e4 = 71.0 / 1920.0, e5 = -17253.0 / 339200.0,
-                 e6 = 22.0 / 525.0, e7 = -1.0 / 40.0;
-constexpr double d1 = -12715105075.0 / 11282082432.0, d3 = 87487479700.0 / 32700410799.0,
-                 d4 = -10690763975.0 / 1880347072.0, d5 = 701980252875.0 / 199316789632.0,
-                 d6 = -1453857185.0 / 822651844.0, d7 = 69997945.0 / 29380423.0;
+/* The tableau lives in __constant__ memory: a DFMA/DMUL then reads its coefficient straight from the constant
+ * bank (c[3][..] operand).  As constexpr literals every coefficient costs two UMOVs per use -- 20 % of all issued
+ * instructions in the first profile (profiles/r1_dopri5_vdp.md). */
+struct Tab {
+    double c2, c3, c4, c5;
+    double a21, a31, a32, a41, a42, a43, a51, a52, a53, a54, a61, a62, a63, a64, a65, a71, a73, a74, a75, a76;
+    double e1, e3, e4, e5, e6, e7;
+    double d1, d3, d4, d5, d6, d7;
+};
+static __constant__ Tab T = {
+    0.2, 0.3, 0.8, 8.0 / 9.0,
+    0.2, 3.0 / 40.0, 9.0 / 40.0, 44.0 / 45.0, -56.0 / 15.0, 32.0 / 9.0, 19372.0 / 6561.0, -25360.0 / 2187.0,
+    64448.0 / 6561.0, -212.0 / 729.0, 9017.0 / 3168.0, -355.0 / 33.0, 46732.0 / 5247.0, 49.0 / 176.0,
+    -5103.0 / 18656.0, 35.0 / 384.0, 500.0 / 1113.0, 125.0 / 192.0, -2187.0 / 6784.0, 11.0 / 84.0,
+    71.0 / 57600.0, -71.0 / 16695.0, 71.0 / 1920.0, -17253.0 / 339200.0, 22.0 / 525.0, -1.0 / 40.0,
+    -12715105075.0 / 11282082432.0, 87487479700.0 / 32700410799.0, -10690763975.0 / 1880347072.0,
+    701980252875.0 / 199316789632.0, -1453857185.0 / 822651844.0, 69997945.0 / 29380423.0};
 constexpr double uround = 2.3e-16; /* dopri5.f:253-254 */
 }  // namespace dp
 
@@ -468,7 +474,12 @@ struct Dopri5 {
     Lane<M> L;
     double k1[N];
     double h, hmax;
-    double facold;             /* STRICT: FACOLD; FAST: FACOLD**2 */
+    double facold;             /* STRICT: FACOLD */
+#if !AENS_STRICT
+    /* FAST: the controller works on lg2 of the squared error norm: fac = 2^lf, hnew = h * 2^-lf */
+    float lfacold;             /* beta/2 * lg2(max(err^2, 1e-8)) */
+    float c_expo1h, c_betah, c_lsafe, c_lfacc1, c_lfacc2;
+#endif
     double cont[DENSE ? 5 * N : 1], told, hstep;
     int nstep, naccpt;         /* per dopri5() call, i.e. per segment */
     bool last, reject;
@@ -520,10 +531,14 @@ struct Dopri5 {
     AENS_DEV void seg_init(const aens_args_t &a, long long idx) {
         seg_init_events(L);
         hmax = dabs((a.o.maxh == 0.0) ? (a.tf - L.t) : a.o.maxh); /* dopri5.f:301-305, :392 */
-#if AENS_STRICT
         facold = 1.0e-4;
-#else
-        facold = 1.0e-8;
+#if !AENS_STRICT
+        c_expo1h = 0.5f * (float)(0.2 - a.o.beta * 0.75);
+        c_betah = 0.5f * (float)a.o.beta;
+        c_lsafe = -flg2((float)a.o.safe);
+        c_lfacc1 = -flg2((float)a.o.fac1);
+        c_lfacc2 = -flg2((float)a.o.fac2);
+        lfacold = c_betah * flg2(1.0e-8f);
 #endif
         last = false;
         reject = false;
@@ -546,42 +561,50 @@ struct Dopri5 {
     }
 
     AENS_DEV int attempt(const aens_args_t &a, long long idx) {
-        using namespace dp;
+        using dp::T;
+        using dp::uround;
         if (nstep > a.o.maxsteps) { L.status = AENS_ST_MAXSTEPS; return AENS_R_ERROR; }
-        if (0.1 * dabs(h) <= dabs(L.t) * uround) { L.status = AENS_ST_STEP_TOO_SMALL; return AENS_R_ERROR; }
         const double x = L.t;
+#if AENS_STRICT
+        if (0.1 * dabs(h) <= dabs(x) * uround) { L.status = AENS_ST_STEP_TOO_SMALL; return AENS_R_ERROR; }
         if ((x + 1.01 * h - a.tf) > 0.0) { h = a.tf - x; last = true; }
+#else
+        if (dabs(h) <= dabs(x) * (10.0 * uround)) { L.status = AENS_ST_STEP_TOO_SMALL; return AENS_R_ERROR; }
+        if (fma(1.01, h, x) > a.tf) { h = a.tf - x; last = true; }
+#endif
         nstep += 1;
         L.st[AENS_STAT_NSTEPSTOTAL] += 1;
         double k2[N], k3[N], k4[N], k5[N], k6[N], y1[N];
 #pragma unroll
-        for (int i = 0; i < N; ++i) y1[i] = L.y[i] + h * a21 * k1[i];
-        L.rhs(x + c2 * h, y1, k2);
+        for (int i = 0; i < N; ++i) y1[i] = L.y[i] + h * T.a21 * k1[i];
+        L.rhs(x + T.c2 * h, y1, k2);
 #pragma unroll
-        for (int i = 0; i < N; ++i) y1[i] = L.y[i] + h * (a31 * k1[i] + a32 * k2[i]);
-        L.rhs(x + c3 * h, y1, k3);
+        for (int i = 0; i < N; ++i) y1[i] = L.y[i] + h * (T.a31 * k1[i] + T.a32 * k2[i]);
+        L.rhs(x + T.c3 * h, y1, k3);
 #pragma unroll
-        for (int i = 0; i < N; ++i) y1[i] = L.y[i] + h * (a41 * k1[i] + a42 * k2[i] + a43 * k3[i]);
-        L.rhs(x + c4 * h, y1, k4);
-#pragma unroll
-        for (int i = 0; i < N; ++i) y1[i] = L.y[i] + h * (a51 * k1[i] + a52 * k2[i] + a53 * k3[i] + a54 * k4[i]);
-        L.rhs(x + c5 * h, y1, k5);
+        for (int i = 0; i < N; ++i) y1[i] = L.y[i] + h * (T.a41 * k1[i] + T.a42 * k2[i] + T.a43 * k3[i]);
+        L.rhs(x + T.c4 * h, y1, k4);
 #pragma unroll
         for (int i = 0; i < N; ++i)
-            y1[i] = L.y[i] + h * (a61 * k1[i] + a62 * k2[i] + a63 * k3[i] + a64 * k4[i] + a65 * k5[i]);
+            y1[i] = L.y[i] + h * (T.a51 * k1[i] + T.a52 * k2[i] + T.a53 * k3[i] + T.a54 * k4[i]);
+        L.rhs(x + T.c5 * h, y1, k5);
+#pragma unroll
+        for (int i = 0; i < N; ++i)
+            y1[i] = L.y[i] + h * (T.a61 * k1[i] + T.a62 * k2[i] + T.a63 * k3[i] + T.a64 * k4[i] + T.a65 * k5[i]);
         const double xph = x + h;
         L.rhs(xph, y1, k6);
 #pragma unroll
         for (int i = 0; i < N; ++i)
-            y1[i] = L.y[i] + h * (a71 * k1[i] + a73 * k3[i] + a74 * k4[i] + a75 * k5[i] + a76 * k6[i]);
+            y1[i] = L.y[i] + h * (T.a71 * k1[i] + T.a73 * k3[i] + T.a74 * k4[i] + T.a75 * k5[i] + T.a76 * k6[i]);
         L.rhs(xph, y1, k2); /* FSAL stage kept in K2 */
         L.st[AENS_STAT_NFCNS] += 6;
         double c4v[DENSE ? N : 1];
         double err2 = 0.0;
 #pragma unroll
         for (int i = 0; i < N; ++i) {
-            if (DENSE) c4v[i] = h * (d1 * k1[i] + d3 * k3[i] + d4 * k4[i] + d5 * k5[i] + d6 * k6[i] + d7 * k2[i]);
-            const double ei = (e1 * k1[i] + e3 * k3[i] + e4 * k4[i] + e5 * k5[i] + e6 * k6[i] + e7 * k2[i]) * h;
+            if (DENSE)
+                c4v[i] = h * (T.d1 * k1[i] + T.d3 * k3[i] + T.d4 * k4[i] + T.d5 * k5[i] + T.d6 * k6[i] + T.d7 * k2[i]);
+            const double ei = (T.e1 * k1[i] + T.e3 * k3[i] + T.e4 * k4[i] + T.e5 * k5[i] + T.e6 * k6[i] + T.e7 * k2[i]) * h;
             const double sk = a.o.atol[i] + a.o.rtol * dmax(dabs(L.y[i]), dabs(y1[i]));
 #if AENS_STRICT
             const double q = ei / sk;
@@ -606,22 +629,22 @@ struct Dopri5 {
         else hnew = h / dmin(facc1, fac11 / a.o.safe);
 #else
         {
-            /* controller in fp32 on the squared norm: err^e = (err2)^(e/2) */
+            /* Hairer's PI controller in the log2 domain, on the squared norm e2 = err^2 (err^e = 2^(e/2 lg2 e2)):
+             *   accept:  lg2 fac = clamp(expo1 lg2 err - beta lg2 facold - lg2 safe, lg2 facc2, lg2 facc1)
+             *   reject:  lg2 fac = min(lg2 facc1, expo1 lg2 err - lg2 safe)          hnew = h * 2^(-lg2 fac)
+             * one MUFU.LG2 and one MUFU.EX2 per attempt; they steer h only, the accept test stays fp64. */
             const double e2 = err2 * (1.0 / N);
-            const float expo1h = 0.5f * (float)(0.2 - a.o.beta * 0.75), betah = 0.5f * (float)a.o.beta;
-            const float facc1 = 1.0f / (float)a.o.fac1, facc2 = 1.0f / (float)a.o.fac2;
-            const float rsafe = 1.0f / (float)a.o.safe;
-            const float fac11 = fpow((float)e2, expo1h);
             accept = (e2 <= 1.0);
-            float fac;
+            const float le2 = flg2((float)e2);
+            const float l11 = fmaf(c_expo1h, le2, c_lsafe);
+            float lf;
             if (accept) {
-                fac = __fdividef(fac11, fpow((float)facold, betah));
-                fac = fmaxf(facc2, fminf(facc1, fac * rsafe));
-                facold = dmax(e2, 1.0e-8);
+                lf = fmaxf(c_lfacc2, fminf(c_lfacc1, l11 - lfacold));
+                lfacold = c_betah * fmaxf(le2, -26.575424759098897f); /* max(err, 1e-4) */
             } else {
-                fac = fminf(facc1, fac11 * rsafe);
+                lf = fminf(c_lfacc1, l11);
             }
-            hnew = h * (double)__fdividef(1.0f, fac);
+            hnew = h * (double)fex2(-lf);
         }
 #endif
         if (accept) {
