@@ -27,6 +27,11 @@ typedef struct {
     int refill_threshold;
     int pad0;
     double tf;
+    /* step-size-controller constants of the FAST Dopri5 build in the log2 domain, computed once on the host
+     * (aens_abi.cu, fill_ctl) so that the kernel reads them as constant-bank operands instead of holding them in
+     * registers: [0] (0.2-0.75 beta)/2  [1] beta/2  [2] -lg2 safe  [3] -lg2 fac1  [4] -lg2 fac2
+     * [5] beta/2 * lg2(1e-8)  (FACOLD = 1e-4 at segment start)  [6] lg2(1e-8)  [7] reserved */
+    float ctl[8];
     aens_opts_t o;
 } aens_args_t;
 

@@ -55,6 +55,16 @@ AENS_DEV float fex2(float x) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(
 AENS_DEV float fpow(float x, float e) { return fex2(e * flg2(x)); }
 /* reciprocal of a strictly positive, normal fp64 number for the error norms: MUFU.RCP64H seed (~2^-23) + one
  * Newton step -> ~2^-46 relative, far below what an accept/reject decision can see */
+/* the argument of larger magnitude, decided on the high words (sign, exponent, 20 mantissa bits): when they tie the
+ * two magnitudes agree to 2^-20, which is all a tolerance scale needs; keeps the compare off the fp64 pipe */
+AENS_DEV double absmax_hi(double a, double b) {
+    return ((__double2hiint(a) & 0x7fffffff) >= (__double2hiint(b) & 0x7fffffff)) ? a : b;
+}
+AENS_DEV double rcp_seed(double b) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b));
+    return r;
+}
 AENS_DEV double rcp_pos(double b) {
     double r;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b));
@@ -245,6 +255,7 @@ struct Euler {
     double yold[DENSE ? N : 1], told, hstep;
     bool pending;
 
+    AENS_DEV void seg_end() {}
     AENS_DEV void load_aux(const aens_args_t &a, long long idx) { inith = a.aux[idx]; }
     AENS_DEV void store_aux(const aens_args_t &a, long long idx) { a.aux[idx] = inith; }
 
@@ -315,6 +326,7 @@ struct RK4 {
     static constexpr int N = M::N;
     Lane<M> L;
     double h;
+    AENS_DEV void seg_end() {}
     AENS_DEV void load_aux(const aens_args_t &, long long) {}
     AENS_DEV void store_aux(const aens_args_t &, long long) {}
     AENS_DEV void interp(double, double *) {}
@@ -357,6 +369,7 @@ struct RK34 {
     double yold[DENSE ? N : 1], flow[DENSE ? N : 1], told, tnext, hstep;
     int it;
 
+    AENS_DEV void seg_end() {}
     AENS_DEV void load_aux(const aens_args_t &, long long) {}
     AENS_DEV void store_aux(const aens_args_t &, long long) {}
     AENS_DEV void interp(double time, double *out) { /* Hermite, runge_kutta.py:715-720; f_high = Y1 */
@@ -467,22 +480,31 @@ static __constant__ Tab T = {
 constexpr double uround = 2.3e-16; /* dopri5.f:253-254 */
 }  // namespace dp
 
+/* lg2 of the state dimension (folds the 1/N of the RMS norm into the log-domain controller) */
+__host__ __device__ constexpr float lg2_int(int n) {
+    return n == 1 ? 0.f : n == 2 ? 1.f : n == 3 ? 1.5849625007f : n == 4 ? 2.f : n == 5 ? 2.3219280949f :
+           n == 6 ? 2.5849625007f : n == 7 ? 2.8073549221f : n == 8 ? 3.f : n == 9 ? 3.1699250014f :
+           n == 10 ? 3.3219280949f : n == 11 ? 3.4594316186f : n == 12 ? 3.5849625007f : n == 13 ? 3.7004397181f :
+           n == 14 ? 3.8073549221f : n == 15 ? 3.9068905956f : 4.f;
+}
+
 template <class M, bool DENSE>
 struct Dopri5 {
     static constexpr bool HAS_DENSE = DENSE;
     static constexpr int N = M::N;
+    /* FAST build, small systems: the stage arguments are accumulated incrementally (see attempt_fast) */
+    static constexpr bool INCREMENTAL = (N <= 4);
     Lane<M> L;
     double k1[N];
     double h, hmax;
-    double facold;             /* STRICT: FACOLD */
-#if !AENS_STRICT
-    /* FAST: the controller works on lg2 of the squared error norm: fac = 2^lf, hnew = h * 2^-lf */
-    float lfacold;             /* beta/2 * lg2(max(err^2, 1e-8)) */
-    float c_expo1h, c_betah, c_lsafe, c_lfacc1, c_lfacc2;
+#if AENS_STRICT
+    double facold;             /* FACOLD */
+#else
+    float lfacold;             /* beta/2 * lg2(max(err^2, 1e-8)): the controller works on lg2 of the squared norm */
 #endif
     double cont[DENSE ? 5 * N : 1], told, hstep;
-    int nstep, naccpt;         /* per dopri5() call, i.e. per segment */
-    bool last, reject;
+    int nstep, naccpt, nrej;   /* per dopri5() call, i.e. per segment; flushed into L.st when the segment ends */
+    int last, reject;          /* flags (int: byte-sized bools cost PRMT packing instructions in the hot loop) */
 
     AENS_DEV void load_aux(const aens_args_t &, long long) {}
     AENS_DEV void store_aux(const aens_args_t &, long long) {}
@@ -494,6 +516,15 @@ struct Dopri5 {
             for (int i = 0; i < N; ++i)
                 out[i] = cont[i] + th * (cont[N + i] + th1 * (cont[2 * N + i] + th * (cont[3 * N + i] + th1 * cont[4 * N + i])));
         }
+    }
+
+    /* called by the kernel whenever attempt() returned anything but CONTINUE, i.e. when dopri5() returns:
+     * NSTEP / NACCPT / NREJCT / NFCN of this call -> the member's statistics (runge_kutta.py:183-186) */
+    AENS_DEV void seg_end() {
+        L.st[AENS_STAT_NSTEPSTOTAL] += nstep;
+        L.st[AENS_STAT_NSTEPS] += naccpt;
+        L.st[AENS_STAT_NERRFAILS] += nrej;
+        L.st[AENS_STAT_NFCNS] += 6 * nstep;
     }
 
     AENS_DEV double hinit(const aens_args_t &a) { /* HINIT with IORD=5, ITOL=1, POSNEG=+1 */
@@ -524,29 +555,65 @@ struct Dopri5 {
         const double der12 = dmax(dabs(der2), sqrt(dnf));
         double h1;
         if (der12 <= 1.0e-15) h1 = dmax(1.0e-6, dabs(hh) * 1.0e-3);
+#if AENS_STRICT
         else h1 = pow(0.01 / der12, 1.0 / 5);
+#else
+        else h1 = (double)fpow((float)(0.01 / der12), 0.2f); /* only a starting guess for the controller */
+#endif
         return dmin(dmin(100 * dabs(hh), h1), hmax);
     }
+
+#if !AENS_STRICT
+    /* dopri5.f:411-414 for the NEXT attempt, evaluated as soon as its step size is known: if x + 1.01 h would pass
+     * tfinal the step goes exactly to tfinal and is the last one.  The bounds depend only on the end point xn of
+     * the step in flight (rem, rem/1.01, hmax: ready long before the error norm), so that one compare + select
+     * follow the controller on the loop-carried critical path.  `use_hmax`: dopri5.f:515 clamps accepted steps to
+     * HMAX.  A rejected step never needs the clamp: its hnew < h and h already satisfied the bounds at the same x. */
+    struct Bounds { double cap, alt; bool lastable; };
+    AENS_DEV Bounds next_bounds(const aens_args_t &a, double xn, bool use_hmax) const {
+        const double rem = a.tf - xn;
+        const double b101 = rem * (1.0 / 1.01);
+        const bool hm = use_hmax && (hmax < b101);
+        Bounds b;
+        b.cap = hm ? hmax : b101;
+        b.alt = hm ? hmax : rem;
+        b.lastable = !hm;
+        return b;
+    }
+    AENS_DEV void clamp_next(const Bounds &b, double hnew, bool accept) {
+        const bool over = accept && (hnew > b.cap);
+        h = over ? b.alt : hnew;
+        last = over && b.lastable;
+    }
+    /* dopri5.f:409 `0.1 |h| <= |x| uround` (uround = 2.3e-16, i.e. |h| <= |x| 2^-48.6), tested on the exponents only:
+     * exponent(h) + 50 <= exponent(x) implies |h| < |x| 2^-49, so every member flagged here is also flagged by the
+     * reference; one whose h sits within a factor 2 above that is flagged an attempt or two later, after the
+     * controller has shrunk h once more.  Keeps the test off the fp64 pipe. */
+    AENS_DEV bool step_too_small(double x) const {
+        const int eh = (__double2hiint(h) >> 20) & 0x7ff, ex = (__double2hiint(x) >> 20) & 0x7ff;
+        return eh + 50 <= ex;
+    }
+#endif
 
     AENS_DEV void seg_init(const aens_args_t &a, long long idx) {
         seg_init_events(L);
         hmax = dabs((a.o.maxh == 0.0) ? (a.tf - L.t) : a.o.maxh); /* dopri5.f:301-305, :392 */
+#if AENS_STRICT
         facold = 1.0e-4;
-#if !AENS_STRICT
-        c_expo1h = 0.5f * (float)(0.2 - a.o.beta * 0.75);
-        c_betah = 0.5f * (float)a.o.beta;
-        c_lsafe = -flg2((float)a.o.safe);
-        c_lfacc1 = -flg2((float)a.o.fac1);
-        c_lfacc2 = -flg2((float)a.o.fac2);
-        lfacold = c_betah * flg2(1.0e-8f);
+#else
+        lfacold = a.ctl[5];
 #endif
         last = false;
         reject = false;
         nstep = 0;
         naccpt = 0;
+        nrej = 0;
         L.rhs(L.t, L.y, k1);
         h = a.o.inith;
         if (h == 0.0) h = hinit(a);
+#if !AENS_STRICT
+        clamp_next(next_bounds(a, L.t, false), h, true);
+#endif
         L.st[AENS_STAT_NFCNS] += 2;
         /* first SOLOUT call (XOLD = X, dopri5.f:399-404): Assimulo runs the locator on a zero-length interval --
          * one more g evaluation at the very same point, never an event -- and reports grid rows <= t */
@@ -561,19 +628,23 @@ struct Dopri5 {
     }
 
     AENS_DEV int attempt(const aens_args_t &a, long long idx) {
+#if AENS_STRICT
+        return attempt_ref(a, idx);
+#else
+        return attempt_fast(a, idx);
+#endif
+    }
+
+#if AENS_STRICT
+    /* DOPCOR in the reference's operation order (compiled with --fmad=false) */
+    AENS_DEV int attempt_ref(const aens_args_t &a, long long idx) {
         using dp::T;
         using dp::uround;
         if (nstep > a.o.maxsteps) { L.status = AENS_ST_MAXSTEPS; return AENS_R_ERROR; }
         const double x = L.t;
-#if AENS_STRICT
         if (0.1 * dabs(h) <= dabs(x) * uround) { L.status = AENS_ST_STEP_TOO_SMALL; return AENS_R_ERROR; }
         if ((x + 1.01 * h - a.tf) > 0.0) { h = a.tf - x; last = true; }
-#else
-        if (dabs(h) <= dabs(x) * (10.0 * uround)) { L.status = AENS_ST_STEP_TOO_SMALL; return AENS_R_ERROR; }
-        if (fma(1.01, h, x) > a.tf) { h = a.tf - x; last = true; }
-#endif
         nstep += 1;
-        L.st[AENS_STAT_NSTEPSTOTAL] += 1;
         double k2[N], k3[N], k4[N], k5[N], k6[N], y1[N];
 #pragma unroll
         for (int i = 0; i < N; ++i) y1[i] = L.y[i] + h * T.a21 * k1[i];
@@ -597,7 +668,6 @@ struct Dopri5 {
         for (int i = 0; i < N; ++i)
             y1[i] = L.y[i] + h * (T.a71 * k1[i] + T.a73 * k3[i] + T.a74 * k4[i] + T.a75 * k5[i] + T.a76 * k6[i]);
         L.rhs(xph, y1, k2); /* FSAL stage kept in K2 */
-        L.st[AENS_STAT_NFCNS] += 6;
         double c4v[DENSE ? N : 1];
         double err2 = 0.0;
 #pragma unroll
@@ -606,50 +676,21 @@ struct Dopri5 {
                 c4v[i] = h * (T.d1 * k1[i] + T.d3 * k3[i] + T.d4 * k4[i] + T.d5 * k5[i] + T.d6 * k6[i] + T.d7 * k2[i]);
             const double ei = (T.e1 * k1[i] + T.e3 * k3[i] + T.e4 * k4[i] + T.e5 * k5[i] + T.e6 * k6[i] + T.e7 * k2[i]) * h;
             const double sk = a.o.atol[i] + a.o.rtol * dmax(dabs(L.y[i]), dabs(y1[i]));
-#if AENS_STRICT
             const double q = ei / sk;
             err2 = err2 + q * q;
-#else
-            const double q = ei * rcp_pos(sk);
-            err2 = fma(q, q, err2);
-#endif
         }
-        double hnew;
-        bool accept;
-#if AENS_STRICT
         const double err = sqrt(err2 / N);
         const double expo1 = 0.2 - a.o.beta * 0.75;
         const double facc1 = 1.0 / a.o.fac1, facc2 = 1.0 / a.o.fac2;
         const double fac11 = pow(err, expo1);
         double fac = fac11 / pow(facold, a.o.beta);
         fac = dmax(facc2, dmin(facc1, fac / a.o.safe));
-        hnew = h / fac;
-        accept = (err <= 1.0);
+        double hnew = h / fac;
+        const bool accept = (err <= 1.0);
         if (accept) facold = dmax(err, 1.0e-4);
         else hnew = h / dmin(facc1, fac11 / a.o.safe);
-#else
-        {
-            /* Hairer's PI controller in the log2 domain, on the squared norm e2 = err^2 (err^e = 2^(e/2 lg2 e2)):
-             *   accept:  lg2 fac = clamp(expo1 lg2 err - beta lg2 facold - lg2 safe, lg2 facc2, lg2 facc1)
-             *   reject:  lg2 fac = min(lg2 facc1, expo1 lg2 err - lg2 safe)          hnew = h * 2^(-lg2 fac)
-             * one MUFU.LG2 and one MUFU.EX2 per attempt; they steer h only, the accept test stays fp64. */
-            const double e2 = err2 * (1.0 / N);
-            accept = (e2 <= 1.0);
-            const float le2 = flg2((float)e2);
-            const float l11 = fmaf(c_expo1h, le2, c_lsafe);
-            float lf;
-            if (accept) {
-                lf = fmaxf(c_lfacc2, fminf(c_lfacc1, l11 - lfacold));
-                lfacold = c_betah * fmaxf(le2, -26.575424759098897f); /* max(err, 1e-4) */
-            } else {
-                lf = fminf(c_lfacc1, l11);
-            }
-            hnew = h * (double)fex2(-lf);
-        }
-#endif
         if (accept) {
             naccpt += 1;
-            L.st[AENS_STAT_NSTEPS] += 1;
             /* (stiffness detection dopri5.f:474-494 only prints under Assimulo's IPRINT: omitted) */
 #pragma unroll
             for (int i = 0; i < N; ++i) {
@@ -675,12 +716,203 @@ struct Dopri5 {
             reject = false;
         } else {
             reject = true;
-            if (naccpt >= 1) L.st[AENS_STAT_NERRFAILS] += 1;
+            if (naccpt >= 1) nrej += 1;
             last = false;
         }
         h = hnew;
         return AENS_R_CONTINUE;
     }
+#else
+    /* DOPCOR re-associated for the fp64 pipe of sm_100a (measured, profiles/r1_fp64_pipe.md: a DFMA with three
+     * distinct register operands issues at 11/12 rate with a 12-cycle dependent latency, one with a constant-bank
+     * operand at full rate with 8 cycles):
+     *  - small systems accumulate every later stage argument as soon as h*k_j exists,
+     *        A_s += a_sj * (h k_j)  for all s > j,   E += e_j (h k_j),   D += d_j (h k_j)
+     *    -- the same multiply-add count as the row-by-row sums of dopri5.f:421-448, but each is a
+     *    constant-bank-operand DFMA, they are mutually independent, and only ONE of them separates two
+     *    consecutive right-hand-side evaluations on the critical path;
+     *  - the error norm scales with the MUFU.RCP64H seed of 1/sk (2^-23 relative: a perturbation of the
+     *    tolerance, not of the solution); the accept test err^2 <= 1 itself is evaluated in fp64;
+     *  - Hairer's PI controller runs in the log2 domain in fp32 (one MUFU.LG2 + one MUFU.EX2 per attempt);
+     *  - accept/reject commits by select, the end-point clamp of the next step is hoisted (clamp_next). */
+    AENS_DEV int attempt_fast(const aens_args_t &a, long long idx) {
+        using dp::T;
+        using dp::uround;
+        const double x = L.t;
+        const bool small = step_too_small(x);
+        if ((nstep > a.o.maxsteps) | small) { /* dopri5.f:405-410 */
+            L.status = (nstep > a.o.maxsteps) ? AENS_ST_MAXSTEPS : AENS_ST_STEP_TOO_SMALL;
+            return AENS_R_ERROR;
+        }
+        nstep += 1;
+        const double xph = x + h;
+        const Bounds nb = next_bounds(a, xph, true);
+        double y1[N], k2[N], E[N], hk1[N], hk7[DENSE ? N : 1], D[DENSE ? N : 1];
+        if constexpr (INCREMENTAL) {
+            double A3[N], A4[N], A5[N], A6[N], hk[N], kk[N];
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+                hk1[i] = h * k1[i];
+                kk[i] = fma(T.a21, hk1[i], L.y[i]); /* stage-2 argument */
+                A3[i] = fma(T.a31, hk1[i], L.y[i]);
+                A4[i] = fma(T.a41, hk1[i], L.y[i]);
+                A5[i] = fma(T.a51, hk1[i], L.y[i]);
+                A6[i] = fma(T.a61, hk1[i], L.y[i]);
+                y1[i] = fma(T.a71, hk1[i], L.y[i]);
+                E[i] = T.e1 * hk1[i];
+                if (DENSE) D[i] = T.d1 * hk1[i];
+            }
+            L.rhs(fma(T.c2, h, x), kk, k2);
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+                hk[i] = h * k2[i];
+                A3[i] = fma(T.a32, hk[i], A3[i]);
+                A4[i] = fma(T.a42, hk[i], A4[i]);
+                A5[i] = fma(T.a52, hk[i], A5[i]);
+                A6[i] = fma(T.a62, hk[i], A6[i]);
+            }
+            L.rhs(fma(T.c3, h, x), A3, kk);
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+                hk[i] = h * kk[i];
+                A4[i] = fma(T.a43, hk[i], A4[i]);
+                A5[i] = fma(T.a53, hk[i], A5[i]);
+                A6[i] = fma(T.a63, hk[i], A6[i]);
+                y1[i] = fma(T.a73, hk[i], y1[i]);
+                E[i] = fma(T.e3, hk[i], E[i]);
+                if (DENSE) D[i] = fma(T.d3, hk[i], D[i]);
+            }
+            L.rhs(fma(T.c4, h, x), A4, kk);
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+                hk[i] = h * kk[i];
+                A5[i] = fma(T.a54, hk[i], A5[i]);
+                A6[i] = fma(T.a64, hk[i], A6[i]);
+                y1[i] = fma(T.a74, hk[i], y1[i]);
+                E[i] = fma(T.e4, hk[i], E[i]);
+                if (DENSE) D[i] = fma(T.d4, hk[i], D[i]);
+            }
+            L.rhs(fma(T.c5, h, x), A5, kk);
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+                hk[i] = h * kk[i];
+                A6[i] = fma(T.a65, hk[i], A6[i]);
+                y1[i] = fma(T.a75, hk[i], y1[i]);
+                E[i] = fma(T.e5, hk[i], E[i]);
+                if (DENSE) D[i] = fma(T.d5, hk[i], D[i]);
+            }
+            L.rhs(xph, A6, kk);
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+                hk[i] = h * kk[i];
+                y1[i] = fma(T.a76, hk[i], y1[i]);
+                E[i] = fma(T.e6, hk[i], E[i]);
+                if (DENSE) D[i] = fma(T.d6, hk[i], D[i]);
+            }
+            L.rhs(xph, y1, k2); /* FSAL stage */
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+                const double hk2 = h * k2[i];
+                E[i] = fma(T.e7, hk2, E[i]);
+                if (DENSE) { D[i] = fma(T.d7, hk2, D[i]); hk7[i] = hk2; }
+            }
+        } else {
+            /* larger systems: N-wide instruction-level parallelism already; row sums keep the live set small */
+            double k3[N], k4[N], k5[N], k6[N];
+#pragma unroll
+            for (int i = 0; i < N; ++i) y1[i] = fma(h * T.a21, k1[i], L.y[i]);
+            L.rhs(fma(T.c2, h, x), y1, k2);
+#pragma unroll
+            for (int i = 0; i < N; ++i) y1[i] = fma(h, fma(T.a32, k2[i], T.a31 * k1[i]), L.y[i]);
+            L.rhs(fma(T.c3, h, x), y1, k3);
+#pragma unroll
+            for (int i = 0; i < N; ++i) y1[i] = fma(h, fma(T.a43, k3[i], fma(T.a42, k2[i], T.a41 * k1[i])), L.y[i]);
+            L.rhs(fma(T.c4, h, x), y1, k4);
+#pragma unroll
+            for (int i = 0; i < N; ++i)
+                y1[i] = fma(h, fma(T.a54, k4[i], fma(T.a53, k3[i], fma(T.a52, k2[i], T.a51 * k1[i]))), L.y[i]);
+            L.rhs(fma(T.c5, h, x), y1, k5);
+#pragma unroll
+            for (int i = 0; i < N; ++i)
+                y1[i] = fma(h, fma(T.a65, k5[i], fma(T.a64, k4[i], fma(T.a63, k3[i], fma(T.a62, k2[i], T.a61 * k1[i])))),
+                            L.y[i]);
+            L.rhs(xph, y1, k6);
+#pragma unroll
+            for (int i = 0; i < N; ++i)
+                y1[i] = fma(h, fma(T.a76, k6[i], fma(T.a75, k5[i], fma(T.a74, k4[i], fma(T.a73, k3[i], T.a71 * k1[i])))),
+                            L.y[i]);
+            L.rhs(xph, y1, k2); /* FSAL stage kept in K2 */
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+                E[i] = h * fma(T.e7, k2[i], fma(T.e6, k6[i], fma(T.e5, k5[i], fma(T.e4, k4[i], fma(T.e3, k3[i], T.e1 * k1[i])))));
+                if (DENSE) {
+                    D[i] = h * fma(T.d7, k2[i], fma(T.d6, k6[i], fma(T.d5, k5[i], fma(T.d4, k4[i], fma(T.d3, k3[i], T.d1 * k1[i])))));
+                    hk1[i] = h * k1[i];
+                    hk7[i] = h * k2[i];
+                }
+            }
+        }
+        /* error norm dopri5.f:451-461 on the squared scale: err^2 = (1/N) sum (E_i / sk_i)^2 */
+        double err2 = 0.0;
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            const double sk = fma(a.o.rtol, dabs(absmax_hi(L.y[i], y1[i])), a.o.atol[i]);
+            const double q = E[i] * rcp_seed(sk);
+            err2 = fma(q, q, err2);
+        }
+        const bool accept = (err2 <= (double)N);
+        /* Hairer's PI controller in the log2 domain (fac = 2^lf, hnew = h 2^-lf), dopri5.f:463-468,527-529:
+         *   accept:  lf = clamp(expo1 lg2 err - beta lg2 facold - lg2 safe, lg2 facc2, lg2 facc1)
+         *   reject:  lf = min(lg2 facc1, expo1 lg2 err - lg2 safe)
+         * and 'a step after a rejection does not grow' (:516) is lf >= 0. */
+        constexpr float LG2N = lg2_int(N);
+        const float le2 = flg2((float)err2) - LG2N;
+        const float l11 = fmaf(a.ctl[0], le2, a.ctl[2]);
+        float lf = fminf(a.ctl[3], accept ? l11 - lfacold : l11);
+        if (accept) {
+            lf = fmaxf(lf, reject ? 0.0f : a.ctl[4]);
+            lfacold = a.ctl[1] * fmaxf(le2, a.ctl[6]); /* FACOLD = max(err, 1e-4) */
+        }
+        const double hnew = h * (double)fex2(-lf);
+        const bool was_last = last;
+        const double h_step = h;
+        clamp_next(nb, hnew, accept);
+        if (accept) {
+            naccpt += 1;
+            if (DENSE) {
+#pragma unroll
+                for (int i = 0; i < N; ++i) {
+                    const double ydiff = y1[i] - L.y[i];
+                    const double bspl = hk1[i] - ydiff;
+                    cont[i] = L.y[i];
+                    cont[N + i] = ydiff;
+                    cont[2 * N + i] = bspl;
+                    cont[3 * N + i] = ydiff - hk7[i] - bspl;
+                    cont[4 * N + i] = D[i];
+                }
+                told = x;
+                hstep = h_step;
+            }
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+                k1[i] = k2[i];
+                L.y[i] = y1[i];
+            }
+            reject = false;
+            if (M::NG > 0 || DENSE) {
+                const int flag = aens_post_step<M, Dopri5>(*this, L, a, idx, x, xph);
+                if (flag == AENS_R_EVENT) return AENS_R_EVENT;
+            } else {
+                L.t = xph;
+            }
+            if (was_last) return AENS_R_COMPLETE;
+        } else {
+            reject = true;
+            if (naccpt >= 1) nrej += 1;
+        }
+        return AENS_R_CONTINUE;
+    }
+#endif
 };
 
 }  // namespace aens
@@ -725,9 +957,15 @@ __device__ __forceinline__ void aens_run(const aens_args_t &a) {
             s.seg_init(a, idx);
             phase = PH_STEP;
         }
+        /* lanes that are stepping stay in a tight attempt loop until one of them leaves the STEP phase */
+        const unsigned stepmask = __ballot_sync(FULL, phase == PH_STEP);
         if (phase == PH_STEP) {
-            const int r = s.attempt(a, idx);
+            int r;
+            do {
+                r = s.attempt(a, idx);
+            } while (__all_sync(stepmask, r == AENS_R_CONTINUE));
             if (r != AENS_R_CONTINUE) {
+                s.seg_end();
                 bool done = true;
                 if (r == AENS_R_EVENT) {
                     /* explicit_ode.pyx:233-264: log, handle_event, restart the solver (initialize=True) */

@@ -252,6 +252,7 @@ struct Radau5 {
     int st, nsing, naccpt, nsteps;
     bool first, last, reject, new_jac_req, jac_is_fresh;
 
+    AENS_DEV void seg_end() {}
     AENS_DEV void load_aux(const aens_args_t &, long long) {}
     AENS_DEV void store_aux(const aens_args_t &, long long) {}
 
