@@ -25,7 +25,24 @@ typedef struct {
     int ev_slots;
     int n_grid;
     int refill_threshold;
-    int pad0;
+    int reverse;              /* no `order`: fetch members from q_end-1 downwards (cost grows with the index) */
+    long long q_begin, q_end; /* member range [q_begin, q_end) this launch integrates (chunked host pipeline) */
+    /* Direct host I/O (aens_simulate_host, zero-copy mode).  When in_y != NULL a member is fetched from the
+     * caller's member-major arrays -- page-locked host memory mapped into the device address space, read over
+     * PCIe by the warp that is about to integrate it -- instead of from the SoA state; the SoA state, the
+     * parameters and the pristine copy for aens_reset are written from the fetched values.  out_* (each may be
+     * NULL) receive the final values, again member-major and straight into host memory. */
+    const double *in_y;       /* [N][n] */
+    const double *in_p;       /* [N][n_p] */
+    const unsigned char *in_sw; /* [N][n_sw] */
+    double t0;                /* common start time of the fetched members */
+    double *p_store;          /* [n_p][N]   SoA copy of in_p */
+    double *y0_store;         /* [n][N]     pristine state */
+    unsigned char *sw0_store; /* [n_sw][N] */
+    double *out_y;            /* [N][n] */
+    double *out_t;            /* [N] */
+    unsigned char *out_sw;    /* [N][n_sw] */
+    int *out_status;          /* [N] */
     double tf;
     /* step-size-controller constants of the FAST Dopri5 build in the log2 domain, computed once on the host
      * (aens_abi.cu, fill_ctl) so that the kernel reads them as constant-bank operands instead of holding them in

@@ -73,6 +73,36 @@ AENS_DEV double rcp_pos(double b) {
 }
 #endif
 
+/* one member's row of a member-major array [N][K]; 16-byte accesses when the row stride allows (the host side only
+ * selects this path for 16-byte aligned bases): a warp that handles 32 consecutive members then moves one contiguous
+ * 32*K*8-byte block, which matters when the array lives in host memory behind PCIe */
+template <int K>
+AENS_DEV void load_row(const double *base, long long idx, double *out) {
+    const double *r = base + idx * K;
+    if constexpr (K % 2 == 0) {
+#pragma unroll
+        for (int k = 0; k < K / 2; ++k) {
+            const double2 v = reinterpret_cast<const double2 *>(r)[k];
+            out[2 * k] = v.x;
+            out[2 * k + 1] = v.y;
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < K; ++k) out[k] = r[k];
+    }
+}
+template <int K>
+AENS_DEV void store_row(double *base, long long idx, const double *v) {
+    double *r = base + idx * K;
+    if constexpr (K % 2 == 0) {
+#pragma unroll
+        for (int k = 0; k < K / 2; ++k) reinterpret_cast<double2 *>(r)[k] = make_double2(v[2 * k], v[2 * k + 1]);
+    } else {
+#pragma unroll
+        for (int k = 0; k < K; ++k) r[k] = v[k];
+    }
+}
+
 /* ------------------------------------------------------------------------------------------------------- */
 /* Per-member state common to all solvers                                                                   */
 /* ------------------------------------------------------------------------------------------------------- */
@@ -93,16 +123,34 @@ struct Lane {
     AENS_DEV void rhs(double tt, const double *yy, double *yd) { M::rhs(tt, yy, sw, p, yd); }
 
     AENS_DEV void load(const aens_args_t &a, long long idx) {
-        t = a.t[idx];
+        if (a.in_y) { /* zero-copy fetch from the caller's member-major host arrays */
+            load_row<M::N>(a.in_y, idx, y);
+            t = a.t0;
 #pragma unroll
-        for (int i = 0; i < M::N; ++i) y[i] = a.y[(long long)i * a.N + idx];
+            for (int i = 0; i < M::N; ++i) a.y0_store[(long long)i * a.N + idx] = y[i];
+            if (M::NP > 0) {
+                load_row<NP>(a.in_p, idx, p);
 #pragma unroll
-        for (int i = 0; i < M::NP; ++i) p[i] = a.p[(long long)i * a.N + idx];
+                for (int i = 0; i < M::NP; ++i) a.p_store[(long long)i * a.N + idx] = p[i];
+            }
 #pragma unroll
-        for (int i = 0; i < M::NSW; ++i) sw[i] = a.sw[(long long)i * a.N + idx];
+            for (int i = 0; i < M::NSW; ++i) {
+                sw[i] = a.in_sw[idx * M::NSW + i];
+                a.sw0_store[(long long)i * a.N + idx] = sw[i];
+            }
+            gi = 0;
+        } else {
+            t = a.t[idx];
+#pragma unroll
+            for (int i = 0; i < M::N; ++i) y[i] = a.y[(long long)i * a.N + idx];
+#pragma unroll
+            for (int i = 0; i < M::NP; ++i) p[i] = a.p[(long long)i * a.N + idx];
+#pragma unroll
+            for (int i = 0; i < M::NSW; ++i) sw[i] = a.sw[(long long)i * a.N + idx];
+            gi = a.n_grid > 0 ? a.grid_idx[idx] : 0;
+        }
 #pragma unroll
         for (int i = 0; i < AENS_NSTATS; ++i) st[i] = 0;
-        gi = a.n_grid > 0 ? a.grid_idx[idx] : 0;
         status = AENS_ST_COMPLETE;
     }
     AENS_DEV void store(const aens_args_t &a, long long idx) {
@@ -115,6 +163,13 @@ struct Lane {
         for (int i = 0; i < AENS_NSTATS; ++i) a.stats[(long long)i * a.N + idx] = st[i];
         if (a.n_grid > 0) a.grid_idx[idx] = gi;
         a.status[idx] = status;
+        if (a.out_y) store_row<M::N>(a.out_y, idx, y);
+        if (a.out_t) a.out_t[idx] = t;
+        if (a.out_status) a.out_status[idx] = status;
+        if (M::NSW > 0 && a.out_sw) {
+#pragma unroll
+            for (int i = 0; i < M::NSW; ++i) a.out_sw[idx * M::NSW + i] = sw[i];
+        }
     }
 };
 
@@ -568,22 +623,25 @@ struct Dopri5 {
      * tfinal the step goes exactly to tfinal and is the last one.  The bounds depend only on the end point xn of
      * the step in flight (rem, rem/1.01, hmax: ready long before the error norm), so that one compare + select
      * follow the controller on the loop-carried critical path.  `use_hmax`: dopri5.f:515 clamps accepted steps to
-     * HMAX.  A rejected step never needs the clamp: its hnew < h and h already satisfied the bounds at the same x. */
-    struct Bounds { double cap, alt; bool lastable; };
-    AENS_DEV Bounds next_bounds(const aens_args_t &a, double xn, bool use_hmax) const {
-        const double rem = a.tf - xn;
-        const double b101 = rem * (1.0 / 1.01);
-        const bool hm = use_hmax && (hmax < b101);
+     * HMAX (after which the end-point test is repeated with the clamped value).  A rejected step never needs the
+     * clamp: its hnew < h and h already satisfied the bounds at the same x. */
+    struct Bounds { double rem, b101; };
+    AENS_DEV Bounds next_bounds(const aens_args_t &a, double xn) const {
         Bounds b;
-        b.cap = hm ? hmax : b101;
-        b.alt = hm ? hmax : rem;
-        b.lastable = !hm;
+        b.rem = a.tf - xn;
+        b.b101 = b.rem * (1.0 / 1.01);
         return b;
     }
-    AENS_DEV void clamp_next(const Bounds &b, double hnew, bool accept) {
-        const bool over = accept && (hnew > b.cap);
-        h = over ? b.alt : hnew;
-        last = over && b.lastable;
+    /* Both magnitude tests look at the high words only (positive doubles order like their bit patterns; a tie of
+     * the high words means the two agree to 2^-20): a step size that exceeds rem/1.01 or HMAX by less than that is
+     * let through, which costs at most one extra short step at the very end. */
+    AENS_DEV void clamp_next(const Bounds &b, double hnew, bool accept, bool use_hmax) {
+        /* dopri5.f:515 first (accepted steps only), then the end-point test on the clamped value; all selects */
+        const bool big = use_hmax && accept && (__double2hiint(hnew) > __double2hiint(hmax));
+        const double h1 = big ? hmax : hnew;
+        const bool over = accept && (__double2hiint(h1) > __double2hiint(b.b101));
+        h = over ? b.rem : h1;
+        last = over;
     }
     /* dopri5.f:409 `0.1 |h| <= |x| uround` (uround = 2.3e-16, i.e. |h| <= |x| 2^-48.6), tested on the exponents only:
      * exponent(h) + 50 <= exponent(x) implies |h| < |x| 2^-49, so every member flagged here is also flagged by the
@@ -612,7 +670,7 @@ struct Dopri5 {
         h = a.o.inith;
         if (h == 0.0) h = hinit(a);
 #if !AENS_STRICT
-        clamp_next(next_bounds(a, L.t, false), h, true);
+        clamp_next(next_bounds(a, L.t), h, true, false);
 #endif
         L.st[AENS_STAT_NFCNS] += 2;
         /* first SOLOUT call (XOLD = X, dopri5.f:399-404): Assimulo runs the locator on a zero-length interval --
@@ -746,7 +804,7 @@ struct Dopri5 {
         }
         nstep += 1;
         const double xph = x + h;
-        const Bounds nb = next_bounds(a, xph, true);
+        const Bounds nb = next_bounds(a, xph);
         double y1[N], k2[N], E[N], hk1[N], hk7[DENSE ? N : 1], D[DENSE ? N : 1];
         if constexpr (INCREMENTAL) {
             double A3[N], A4[N], A5[N], A6[N], hk[N], kk[N];
@@ -874,43 +932,53 @@ struct Dopri5 {
             lfacold = a.ctl[1] * fmaxf(le2, a.ctl[6]); /* FACOLD = max(err, 1e-4) */
         }
         const double hnew = h * (double)fex2(-lf);
-        const bool was_last = last;
+        const int was_last = last;
         const double h_step = h;
-        clamp_next(nb, hnew, accept);
-        if (accept) {
-            naccpt += 1;
-            if (DENSE) {
-#pragma unroll
-                for (int i = 0; i < N; ++i) {
-                    const double ydiff = y1[i] - L.y[i];
-                    const double bspl = hk1[i] - ydiff;
-                    cont[i] = L.y[i];
-                    cont[N + i] = ydiff;
-                    cont[2 * N + i] = bspl;
-                    cont[3 * N + i] = ydiff - hk7[i] - bspl;
-                    cont[4 * N + i] = D[i];
-                }
-                told = x;
-                hstep = h_step;
-            }
+        clamp_next(nb, hnew, accept, true);
+        if constexpr (M::NG == 0 && !DENSE) {
+            /* final-state-only members: commit by select, no divergent region in the hot loop */
+            naccpt += accept ? 1 : 0;
+            nrej += (!accept && naccpt >= 1) ? 1 : 0;
+            reject = accept ? 0 : 1;
 #pragma unroll
             for (int i = 0; i < N; ++i) {
-                k1[i] = k2[i];
-                L.y[i] = y1[i];
+                k1[i] = accept ? k2[i] : k1[i];
+                L.y[i] = accept ? y1[i] : L.y[i];
             }
-            reject = false;
-            if (M::NG > 0 || DENSE) {
+            L.t = accept ? xph : x;
+            return (accept && was_last) ? AENS_R_COMPLETE : AENS_R_CONTINUE;
+        } else {
+            if (accept) {
+                naccpt += 1;
+                if (DENSE) {
+#pragma unroll
+                    for (int i = 0; i < N; ++i) {
+                        const double ydiff = y1[i] - L.y[i];
+                        const double bspl = hk1[i] - ydiff;
+                        cont[i] = L.y[i];
+                        cont[N + i] = ydiff;
+                        cont[2 * N + i] = bspl;
+                        cont[3 * N + i] = ydiff - hk7[i] - bspl;
+                        cont[4 * N + i] = D[i];
+                    }
+                    told = x;
+                    hstep = h_step;
+                }
+#pragma unroll
+                for (int i = 0; i < N; ++i) {
+                    k1[i] = k2[i];
+                    L.y[i] = y1[i];
+                }
+                reject = 0;
                 const int flag = aens_post_step<M, Dopri5>(*this, L, a, idx, x, xph);
                 if (flag == AENS_R_EVENT) return AENS_R_EVENT;
+                if (was_last) return AENS_R_COMPLETE;
             } else {
-                L.t = xph;
+                reject = 1;
+                if (naccpt >= 1) nrej += 1;
             }
-            if (was_last) return AENS_R_COMPLETE;
-        } else {
-            reject = true;
-            if (naccpt >= 1) nrej += 1;
+            return AENS_R_CONTINUE;
         }
-        return AENS_R_CONTINUE;
     }
 #endif
 };
@@ -930,6 +998,7 @@ __device__ __forceinline__ void aens_run(const aens_args_t &a) {
     S s;
     long long idx = -1;
     int phase = PH_IDLE;
+    bool pending = false; /* a finished member waits in this lane's registers for the warp's next common store point */
     bool drained = false; /* warp-uniform: the queue has no more members */
     for (;;) {
         const unsigned idle_mask = __ballot_sync(FULL, phase == PH_IDLE);
@@ -941,17 +1010,25 @@ __device__ __forceinline__ void aens_run(const aens_args_t &a) {
             if (lane == leader) base = atomicAdd(a.queue, (unsigned long long)nidle);
             base = __shfl_sync(FULL, base, leader);
             if (phase == PH_IDLE) {
-                const long long q = (long long)base + __popc(idle_mask & ((1u << lane) - 1u));
-                if (q < a.N) {
-                    idx = a.order ? (long long)a.order[q] : q;
+                /* results leave the registers here, for all idle lanes of the warp at once: lanes that were fetched
+                 * together hold consecutive members, so their rows form contiguous blocks (SoA state in HBM and, in
+                 * zero-copy mode, the caller's member-major host arrays) */
+                if (pending) {
+                    s.L.store(a, idx);
+                    s.store_aux(a, idx);
+                    pending = false;
+                }
+                const long long q = a.q_begin + (long long)base + __popc(idle_mask & ((1u << lane) - 1u));
+                if (q < a.q_end) {
+                    idx = a.order ? (long long)a.order[q] : (a.reverse ? a.q_end - 1 - (q - a.q_begin) : q);
                     s.L.load(a, idx);
                     s.load_aux(a, idx);
                     /* driver loop test, explicit_ode.pyx:209 */
                     if (s.L.t + eps * aens::dmax(aens::dabs(s.L.t), aens::dabs(a.tf)) < a.tf) phase = PH_SEGINIT;
-                    else { s.L.store(a, idx); s.store_aux(a, idx); }
+                    else pending = true;
                 }
             }
-            if ((long long)base + nidle >= a.N) drained = true;
+            if (a.q_begin + (long long)base + nidle >= a.q_end) drained = true;
         }
         if (phase == PH_SEGINIT) {
             s.seg_init(a, idx);
@@ -994,13 +1071,15 @@ __device__ __forceinline__ void aens_run(const aens_args_t &a) {
                     }
                 }
                 if (done) {
-                    s.L.store(a, idx);
-                    s.store_aux(a, idx);
+                    pending = true;
                     phase = PH_IDLE;
-                    idx = -1;
                 }
             }
         }
+    }
+    if (pending) { /* the warp's last members: every lane is idle here */
+        s.L.store(a, idx);
+        s.store_aux(a, idx);
     }
 }
 

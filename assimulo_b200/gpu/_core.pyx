@@ -68,6 +68,13 @@ cdef extern from "assimulo_cuda.h":
     long long aens_launch_count(const aens_handle_t *h) nogil
     int aens_host_alloc(long long nbytes, void **ptr) nogil
     int aens_host_free(void *ptr) nogil
+    int aens_set_fetch_reverse(aens_handle_t *h, int reverse) nogil
+    int aens_simulate_host(aens_handle_t *h, long long N, const double *y0, const double *p,
+                           const unsigned char *sw0, double t0, double tfinal, double *y_out, double *t_out,
+                           unsigned char *sw_out, int *status_out, int nchunks, long long *sums,
+                           long long *n_not_complete) nogil
+    int aens_get_summary(aens_handle_t *h, long long *sums, long long *n_not_complete) nogil
+    int aens_set_host_mode(aens_handle_t *h, int mode) nogil
 
 STAT_NAMES = ("nsteps", "nfcns", "nerrfails", "njacs", "nlus", "nstatefcns", "nstateevents", "nstepstotal")
 SOLVER_IDS = {"ExplicitEuler": 0, "RungeKutta4": 1, "RungeKutta34": 2, "Dopri5": 3, "Radau5ODE": 4}
@@ -293,6 +300,77 @@ cdef class Handle:
         with nogil:
             rc = aens_simulate(self.h, tfinal)
         self._check(rc)
+
+    def set_host_mode(self, int mode):
+        """0 auto, 1 chunked staging pipeline, 2 zero-copy (raises at simulate_host if the arrays are not mappable)."""
+        self._check(aens_set_host_mode(self.h, mode))
+
+    def set_fetch_reverse(self, bint reverse):
+        self._check(aens_set_fetch_reverse(self.h, reverse))
+
+    def simulate_host(self, y0, p, sw0, double t0, double tfinal, out_y=None, out_t=None, out_sw=None,
+                      out_status=None, int nchunks=8):
+        """aens_simulate_host: upload, integrate and download in one chunk-pipelined call.  y0/p/sw0 as for
+        set_ensemble; out_* are caller-owned C-contiguous arrays (ideally pinned_empty) or None to skip that
+        result.  Returns (statistic sums dict, number of members that did not complete)."""
+        cdef np.ndarray[double, ndim=2, mode="c"] y = np.ascontiguousarray(y0, dtype=np.float64)
+        cdef np.ndarray[double, ndim=2, mode="c"] pp
+        cdef np.ndarray[np.uint8_t, ndim=2, mode="c"] ss
+        cdef const double *pptr = NULL
+        cdef const unsigned char *sptr = NULL
+        cdef long long N = y.shape[0]
+        if y.shape[1] != self.n:
+            raise ValueError("y0 must have shape [N, %d]" % self.n)
+        if self.n_p:
+            pp = np.ascontiguousarray(p, dtype=np.float64)
+            if pp.shape[0] != N or pp.shape[1] != self.n_p:
+                raise ValueError("p must have shape [N, %d]" % self.n_p)
+            pptr = &pp[0, 0]
+        if self.n_sw:
+            ss = np.ascontiguousarray(sw0, dtype=np.uint8)
+            if ss.shape[0] != N or ss.shape[1] != self.n_sw:
+                raise ValueError("sw0 must have shape [N, %d]" % self.n_sw)
+            sptr = &ss[0, 0]
+        cdef double *yo = NULL
+        cdef double *to = NULL
+        cdef unsigned char *so = NULL
+        cdef int *sto = NULL
+        cdef np.ndarray a
+        if out_y is not None:
+            a = out_y
+            assert a.dtype == np.float64 and a.size == N * self.n and a.flags.c_contiguous
+            yo = <double*>np.PyArray_DATA(a)
+        if out_t is not None:
+            a = out_t
+            assert a.dtype == np.float64 and a.size == N and a.flags.c_contiguous
+            to = <double*>np.PyArray_DATA(a)
+        if out_sw is not None and self.n_sw:
+            a = out_sw
+            assert a.dtype == np.uint8 and a.size == N * self.n_sw and a.flags.c_contiguous
+            so = <unsigned char*>np.PyArray_DATA(a)
+        if out_status is not None:
+            a = out_status
+            assert a.dtype == np.intc and a.size == N and a.flags.c_contiguous
+            sto = <int*>np.PyArray_DATA(a)
+        cdef const double *yptr = &y[0, 0]
+        cdef long long sums[8]
+        cdef long long nbad = 0
+        cdef int rc
+        with nogil:
+            rc = aens_simulate_host(self.h, N, yptr, pptr, sptr, t0, tfinal, yo, to, so, sto, nchunks, sums, &nbad)
+        self._check(rc)
+        self.N = N
+        self.n_out = 0
+        return {STAT_NAMES[i]: sums[i] for i in range(8)}, nbad
+
+    def get_summary(self):
+        cdef long long s[8]
+        cdef long long nbad = 0
+        cdef int rc
+        with nogil:
+            rc = aens_get_summary(self.h, s, &nbad)
+        self._check(rc)
+        return {STAT_NAMES[i]: s[i] for i in range(8)}, nbad
 
     def simulate_async(self, double tfinal):
         cdef int rc

@@ -60,7 +60,7 @@ class Batched_Explicit_ODE(object):
             raise Explicit_ODE_Exception("The problem needs to be a subclass of a Batched_Explicit_Problem.")
         self.problem = problem
         self.options = {"arith": "fast", "refill_threshold": 32, "order": None, "event_slots": 16,
-                        "verbosity": 30, "store_event_points": True, "reuse_buffers": False}
+                        "verbosity": 30, "store_event_points": True, "reuse_buffers": False, "host_chunks": None}
         self.supports = {"state_events": False, "interpolated_output": False, "report_continuously": False}
         self.problem_info = {"dim": problem.n, "dimRoot": problem.n_g, "state_events": problem.n_g > 0,
                              "jac_fcn": problem.has_jac, "switches": problem.n_sw > 0}
@@ -76,8 +76,10 @@ class Batched_Explicit_ODE(object):
         self.N = problem.N
         self.y = problem.y0.copy()
         self.sw = problem.sw0.astype(bool)
-        self.status = np.zeros(self.N, dtype=np.intc)
-        self.t_members = np.full(self.N, problem.t0)
+        self._status = None        # per-member arrays are materialised on first access (see the properties)
+        self._t_members = None
+        self._events = None
+        self.n_not_complete = 0
         self.t_sol, self.y_sol = [], []
         self.elapsed_kernel_ms = None
 
@@ -130,7 +132,8 @@ class Batched_Explicit_ODE(object):
         if sw0 is not None:
             self.sw = np.ascontiguousarray(np.broadcast_to(np.asarray(sw0, dtype=bool).reshape(-1, self.problem.n_sw),
                                                            (self.N, self.problem.n_sw)))
-        self.t_members = np.full(self.N, self.t)
+        self._status, self._t_members, self._events = None, None, None
+        self.n_not_complete = 0
         self._dirty = True
 
     def reset(self):
@@ -171,17 +174,15 @@ class Batched_Explicit_ODE(object):
         self.problem.initialize(self)
         self.initialize()
         h = self._get_handle()
-        if self._dirty:
-            h.set_ensemble(self.y, self.problem.p0 if self.problem.n_p else None,
-                           self.sw.astype(np.uint8) if self.problem.n_sw else None, self.t)
-            self._dirty = False
+        order = self.options["order"]
+        reverse = isinstance(order, str) and order == "descending"
+        if isinstance(order, str):
+            if order not in ("ascending", "descending"):
+                raise AssimuloException("order must be None, 'ascending', 'descending' or a permutation of range(N).")
+            order = None
+        h.set_fetch_reverse(reverse)
         h.set_opts(self._opts_dict())
-        h.set_output(output_list, int(self.options["event_slots"]))
-        h.set_schedule(int(self.options["refill_threshold"]), self.options["order"])
-        self.problem.handle_result(self, t0, self.y)
-        h.simulate(tfinal)
-        self._launched = True
-        self.elapsed_kernel_ms = h.last_kernel_ms()
+        pin = None
         if self.options["reuse_buffers"]:
             # page-locked result buffers allocated once and overwritten by every simulate() call: rows returned
             # by an earlier call alias them (documented trade: no ensemble-sized allocation or copy per call)
@@ -189,13 +190,45 @@ class Batched_Explicit_ODE(object):
                 c = _core()
                 self._pin = (c.pinned_empty((self.N,), np.float64), c.pinned_empty((self.N, self._leny), np.float64),
                              c.pinned_empty((self.N,), np.intc))
-            tm, y, sw, status = h.get_final(out_t=self._pin[0], out_y=self._pin[1], out_status=self._pin[2])
+            pin = self._pin
+        self.problem.handle_result(self, t0, self.y)
+        if self._dirty and output_list is None and order is None:
+            # host -> device -> host in one chunk-pipelined call (aens_simulate_host): uploads, kernels and
+            # downloads of consecutive member ranges overlap.  Only y comes back eagerly; the per-member end times
+            # and status codes are fetched on first access -- the summary says whether any member did not complete.
+            nch = self.options["host_chunks"] or max(1, min(32, self.N >> 19))
+            h.set_output(None, int(self.options["event_slots"]))
+            h.set_schedule(int(self.options["refill_threshold"]), None)
+            y = pin[1] if pin is not None else np.empty((self.N, self._leny))
+            sw = np.empty((self.N, self.problem.n_sw), dtype=np.uint8) if self.problem.n_sw else None
+            sums, nbad = h.simulate_host(self.y, self.problem.p0 if self.problem.n_p else None,
+                                         self.sw.astype(np.uint8) if self.problem.n_sw else None, self.t, tfinal,
+                                         out_y=y, out_sw=sw, nchunks=int(nch))
+            self._dirty = False
+            self._launched = True
+            self.elapsed_kernel_ms = None
+            self.y = y
+            self._status, self._t_members, self._events = None, None, None
         else:
-            tm, y, sw, status = h.get_final()
-        self.t_members, self.y, self.status = tm, y, status
+            if self._dirty:
+                h.set_ensemble(self.y, self.problem.p0 if self.problem.n_p else None,
+                               self.sw.astype(np.uint8) if self.problem.n_sw else None, self.t)
+                self._dirty = False
+            h.set_output(output_list, int(self.options["event_slots"]))
+            h.set_schedule(int(self.options["refill_threshold"]), order)
+            h.simulate(tfinal)
+            self._launched = True
+            self.elapsed_kernel_ms = h.last_kernel_ms()
+            if pin is not None:
+                tm, y, sw, status = h.get_final(out_t=pin[0], out_y=pin[1], out_status=pin[2])
+            else:
+                tm, y, sw, status = h.get_final()
+            self._t_members, self.y, self._status, self._events = tm, y, status, None
+            sums, nbad = h.get_summary()
+        self._tfinal = tfinal
+        self.n_not_complete = int(nbad)
         if sw is not None:
             self.sw = sw.astype(bool)
-        sums = h.get_stats_sum()
         for k in STAT_NAMES:
             self.statistics[k] = int(sums[k])
         if output_list is not None:
@@ -205,14 +238,32 @@ class Batched_Explicit_ODE(object):
         else:
             self.problem.handle_result(self, tfinal, self.y)
         # the ensemble's current time: members that failed or were terminated stopped early (see status)
-        self.t = tfinal if not self.status.any() else float(np.min(self.t_members))
-        if self.problem.n_g > 0:
-            self._events = h.get_events()
+        self.t = tfinal if nbad == 0 else float(np.min(self.t_members))
         self.finalize()
         self.problem.finalize(self)
         if self.options["reuse_buffers"]:
             return self.t_sol, self.y_sol  # list of [N, n] rows, no ensemble-sized stacking copy
         return self.t_sol, np.array(self.y_sol)
+
+    @property
+    def status(self):
+        """Per-member status codes (include/assimulo_cuda.h AENS_ST_*); 0 = reached tfinal."""
+        if self._status is None:
+            if self._launched and self.n_not_complete:
+                self._status = self._handle.get_final(want_y=False, want_sw=False, want_t=False)[3]
+            else:
+                self._status = np.zeros(self.N, dtype=np.intc)
+        return self._status
+
+    @property
+    def t_members(self):
+        """Per-member end times (differ from self.t only for members that failed or were terminated)."""
+        if self._t_members is None:
+            if self._launched and self.n_not_complete:
+                self._t_members = self._handle.get_final(want_y=False, want_sw=False)[0]
+            else:
+                self._t_members = np.full(self.N, self.t)
+        return self._t_members
 
     __call__ = simulate
 
@@ -221,8 +272,13 @@ class Batched_Explicit_ODE(object):
         """(count[N], t_event[N, slots], info[N, slots]): ring of the last `event_slots` state events of each
         member.  info bit 2i: indicator i fired; bit 2i+1: event_info[i] == +1 (else -1), cf.
         src/explicit_ode.pyx:351-357."""
-        return getattr(self, "_events", (np.zeros(self.N, dtype=np.intc), np.zeros((self.N, 0)),
-                                         np.zeros((self.N, 0), dtype=np.intc)))
+        if self._events is None:
+            if self._launched and self.problem.n_g > 0:
+                self._events = self._handle.get_events()
+            else:
+                self._events = (np.zeros(self.N, dtype=np.intc), np.zeros((self.N, 0)),
+                                np.zeros((self.N, 0), dtype=np.intc))
+        return self._events
 
     def event_times(self, member):
         """Chronological event times of one member (at most `event_slots` most recent)."""
@@ -267,11 +323,15 @@ class Batched_Explicit_ODE(object):
     refill_threshold = property(_get_refill, _set_refill)
 
     def _get_order(self):
-        """Optional permutation of range(N): the order in which members are handed to the warps."""
+        """The order in which members are handed to the warps: None / 'ascending' (by index), 'descending' (from the
+        last member down: for ensembles sorted by increasing cost) or a permutation of range(N)."""
         return self.options["order"]
 
     def _set_order(self, v):
-        self.options["order"] = None if v is None else np.ascontiguousarray(v, dtype=np.intc)
+        if v is None or isinstance(v, str):
+            self.options["order"] = v
+        else:
+            self.options["order"] = np.ascontiguousarray(v, dtype=np.intc)
     order = property(_get_order, _set_order)
 
     def _get_event_slots(self):

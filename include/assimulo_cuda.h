@@ -139,6 +139,10 @@ int aens_set_output(aens_handle_t *h, int n_out, const double *t_out, int event_
  * permutation of 0..N-1 giving the fetch order (e.g. most expensive first). */
 int aens_set_schedule(aens_handle_t *h, int refill_threshold, const int *order);
 
+/* No fetch permutation: hand members out from the highest index downwards (reverse != 0) instead of upwards --
+ * for ensembles whose cost grows with the member index (most expensive first, no permutation array to upload). */
+int aens_set_fetch_reverse(aens_handle_t *h, int reverse);
+
 /* Integrates every member from its current time to tfinal (continuation semantics of ODE.simulate,
  * src/ode.pyx:195-196,222).  Synchronous.  Returns AENS_OK even if individual members failed: see status[]. */
 int aens_simulate(aens_handle_t *h, double tfinal);
@@ -147,6 +151,24 @@ int aens_simulate_async(aens_handle_t *h, double tfinal);
 int aens_sync(aens_handle_t *h);
 /* device time of the last aens_simulate[_async] launch in milliseconds (CUDA events on the handle's stream) */
 int aens_last_kernel_ms(aens_handle_t *h, float *ms);
+
+/* aens_set_ensemble + aens_simulate + aens_get_final in ONE call for inputs and results in host memory -- what a
+ * Python loop `for i: Solver(Explicit_Problem(rhs_i, y0_i)).simulate(tfinal)` does, end to end.  The members are
+ * cut into `nchunks` contiguous ranges; host->device copies, kernels and device->host copies of consecutive
+ * ranges overlap on separate CUDA streams.  Outputs (any may be NULL): y_out[N][n], t_out[N], sw_out[N][n_sw],
+ * status_out[N]; sums[AENS_NSTATS] = statistic totals; *n_not_complete = members whose status != AENS_ST_COMPLETE.
+ * Uses the options, event-slot count and fetch direction set on the handle; needs n_out == 0 and no fetch
+ * permutation.  Host arrays should be page-locked (aens_host_alloc) for the copies to overlap. */
+int aens_simulate_host(aens_handle_t *h, long long N, const double *y0, const double *p, const unsigned char *sw0,
+                       double t0, double tfinal, double *y_out, double *t_out, unsigned char *sw_out,
+                       int *status_out, int nchunks, long long *sums, long long *n_not_complete);
+/* How aens_simulate_host moves data: 0 = automatic (zero-copy when every host array is page-locked, mapped and
+ * 16-byte aligned -- ONE kernel launch whose warps read their members' rows from host memory over PCIe when they
+ * fetch them and write the final rows back when they finish; otherwise the chunked staging pipeline),
+ * 1 = always the chunked staging pipeline, 2 = zero-copy or fail. */
+int aens_set_host_mode(aens_handle_t *h, int mode);
+/* statistic totals and the number of members that did not complete, after aens_simulate */
+int aens_get_summary(aens_handle_t *h, long long *sums /*[AENS_NSTATS]*/, long long *n_not_complete);
 
 /* Results (any pointer may be NULL): t[N], y[N][n], sw[N][n_sw], status[N]. */
 int aens_get_final(aens_handle_t *h, double *t, double *y, unsigned char *sw, int *status);
@@ -168,8 +190,9 @@ int aens_device_ptr(aens_handle_t *h, int which, void **ptr, long long *bytes);
 /* CUDA stream of the handle (cudaStream_t as void*) */
 int aens_stream(aens_handle_t *h, void **stream);
 
-/* Page-locked host memory for the caller's arrays: host<->device copies of pinned buffers run at full PCIe rate
- * and asynchronously (the reference has no analogue; its arrays never leave the host). */
+/* Page-locked host memory, mapped into the device address space, for the caller's arrays: host<->device copies of
+ * pinned buffers run at full PCIe rate and asynchronously, and aens_simulate_host can read/write them directly from
+ * the kernel (the reference has no analogue; its arrays never leave the host). */
 int aens_host_alloc(long long bytes, void **ptr);
 int aens_host_free(void *ptr);
 

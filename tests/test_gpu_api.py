@@ -28,7 +28,7 @@ def test_simulate_surface_dopri5():
     assert sim.statistics["nfcns"] == o["stats"]["nfcns"].sum() or abs(
         sim.statistics["nfcns"] - o["stats"]["nfcns"].sum()) <= 0.02 * o["stats"]["nfcns"].sum()
     assert sim.statistics.per_member("nsteps").shape == (N,)
-    assert sim.t == 2.0 and (sim.status == 0).all() and sim.elapsed_kernel_ms > 0
+    assert sim.t == 2.0 and (sim.status == 0).all() and sim.n_not_complete == 0
     sim.print_statistics()
 
 
@@ -250,3 +250,93 @@ def test_full_size_properties_cfg2():
             setattr(sub, k, v)
         sub.simulate(2.0)
         assert rel_err(sub.y, sim.y[perm]) <= (0 if oname == "RungeKutta4" else 1e-12)
+
+
+@pytest.mark.parametrize("mode", [1, 2])
+@pytest.mark.parametrize("N,nchunks", [(1, 1), (33, 4), (1000, 7), (4096, 8), (5000, 64)])
+def test_host_pipeline_equals_the_three_call_path(N, nchunks, mode):
+    """aens_simulate_host -- mode 1: chunked upload / kernels / download on overlapping streams; mode 2: zero-copy,
+    the kernel reads and writes the caller's page-locked host arrays directly -- must give bit-identical states, end
+    times, status codes and statistics to set_ensemble + simulate + get_final, for ragged sizes, any chunk count and
+    both fetch directions."""
+    from assimulo_b200.gpu import _core
+    y0, mu = cases.vdp_sweep(max(N, 2))
+    y0, mu = y0[:N], mu[:N]
+    if mode == 2:
+        y0p, mup = _core.pinned_empty((N, 2)), _core.pinned_empty((N, 1))
+        y0p[:], mup[:] = y0, mu
+        y0, mu = y0p, mup
+    for reverse in (False, True):
+        h = _core.Handle(0)
+        h.set_host_mode(mode)
+        h.set_model_builtin("vdp")
+        h.set_opts({"solver": _core.SOLVER_IDS["Dopri5"], "arith": 0, "rtol": 1e-6, "atol": 1e-6})
+        h.set_fetch_reverse(reverse)
+        h.set_ensemble(y0, mu, None, 0.0)
+        h.set_output(None, 16)
+        h.simulate(2.0)
+        t1, y1, _, st1 = h.get_final()
+        s1 = h.get_stats_sum()
+        n1 = {k: h.get_stats(k) for k in ("nsteps", "nfcns", "nerrfails")}
+        oy, ot, ost = _core.pinned_empty((N, 2)), _core.pinned_empty((N,)), _core.pinned_empty((N,), np.intc)
+        oy[:], ot[:], ost[:] = np.nan, np.nan, -99
+        s2, nbad = h.simulate_host(y0, mu, None, 0.0, 2.0, out_y=oy, out_t=ot, out_status=ost, nchunks=nchunks)
+        assert nbad == 0 and s1 == s2
+        assert np.array_equal(oy, y1) and np.array_equal(ot, t1) and np.array_equal(ost, st1)
+        for k, v in n1.items():
+            assert np.array_equal(h.get_stats(k), v)
+        # summary entry point agrees
+        s3, nb3 = h.get_summary()
+        assert s3 == s2 and nb3 == 0
+        # aens_reset restores the pristine copy written by the pipelined upload
+        h.reset()
+        h.simulate(2.0)
+        assert np.array_equal(h.get_final()[1], y1)
+        h.close()
+
+
+def test_host_pipeline_with_events_switches_and_failures():
+    from assimulo_b200.gpu import Batched_Explicit_Problem, Dopri5
+    N = 3000
+    y0, p, sw0 = cases.ball_sweep(N)
+    o = O.simulate("ball", "Dopri5", y0, p, sw0, tf=3.0, max_ev=16, rtol=1e-6, atol=1e-6)
+    # zero-copy with switches and all outputs, straight through the handle
+    from assimulo_b200.gpu import _core
+    h = _core.Handle(0)
+    h.set_host_mode(2)
+    h.set_model_builtin("ball")
+    h.set_opts({"solver": _core.SOLVER_IDS["Dopri5"], "arith": 1, "rtol": 1e-6, "atol": 1e-6})
+    pin = [_core.pinned_empty((N, 2)), _core.pinned_empty((N, 2)), _core.pinned_empty((N, 2), np.uint8)]
+    pin[0][:], pin[1][:], pin[2][:] = y0, p, sw0
+    oy, ot = _core.pinned_empty((N, 2)), _core.pinned_empty((N,))
+    osw, ost = _core.pinned_empty((N, 2), np.uint8), _core.pinned_empty((N,), np.intc)
+    sums, nbad = h.simulate_host(pin[0], pin[1], pin[2], 0.0, 3.0, out_y=oy, out_t=ot, out_sw=osw, out_status=ost)
+    assert nbad == 0 and (ost == 0).all() and (ot == 3.0).all()
+    assert rel_err(oy, o["y"]) <= 1e-5 and np.array_equal(osw, o["sw"])
+    assert sums["nstateevents"] == int(o["stats"]["nstateevents"].sum())
+    cnt = h.get_events()[0]
+    assert np.array_equal(cnt, o["stats"]["nstateevents"])
+    with pytest.raises(_core.AensError):                 # pageable arrays cannot be mapped: mode 2 refuses
+        h.simulate_host(y0, p, sw0, 0.0, 3.0, out_y=oy)
+    h.close()
+    sim = Dopri5(Batched_Explicit_Problem(model="ball", y0=y0, p0=p, sw0=sw0))
+    sim.options["host_chunks"] = 5
+    sim.order = "descending"
+    sim.simulate(3.0)                                   # first call: ensemble is dirty -> pipelined path
+    assert sim.elapsed_kernel_ms is None and sim.n_not_complete == 0 and (sim.status == 0).all()
+    assert rel_err(sim.y, o["y"]) <= 1e-5 and np.array_equal(sim.sw, o["sw"].astype(bool))
+    cnt, te, info = sim.event_log
+    assert np.array_equal(cnt, o["stats"]["nstateevents"])
+    m = np.isfinite(o["ev_t"])
+    assert np.max(np.abs(te[m] - o["ev_t"][m])) < 1e-9
+    assert sim.statistics["nstateevents"] == int(o["stats"]["nstateevents"].sum())
+    # members that fail are counted by the summary and their codes fetched lazily
+    y0v, mu = cases.vdp_sweep(512)
+    sim = Dopri5(Batched_Explicit_Problem(model="vdp", y0=y0v, p0=mu))
+    sim.maxsteps = 40
+    sim.simulate(2.0)
+    ora = O.simulate("vdp", "Dopri5", y0v, mu, tf=2.0, rtol=1e-6, atol=1e-6, maxsteps=40)
+    bad = ora["status"] != 0
+    assert sim.n_not_complete == int(bad.sum()) > 0
+    assert ((sim.status == -2) == bad).all() and (sim.t_members[bad] < 2.0).all() and sim.t < 2.0
+    assert (sim.t_members[~bad] == 2.0).all()
