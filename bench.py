@@ -190,8 +190,66 @@ def workload_config(a, n_total):
             "members_total": n_total, "members_per_gpu": a.members, "solver": "Dopri5", "model": "vdp",
             "arith": "fast", "l2": "per-GPU inputs+outputs %.0f MB > 126 MB L2 (no flush needed)"
                                    % (a.members * (3 + 3 + 1.5 + 4) * 8 / 1e6),
+            "fetch": "descending member index (cost grows with mu), 32-member batches per warp",
             "parallelism": "members sharded over %d GPU(s), 32-member chunks dealt round-robin, no data-path "
                            "collective; one all_gather of final states at the end (not in the timed region)" % a.gpus}
+
+
+# ------------------------------------------------------------------------------------------------------
+# the other BASELINE.json configurations (N = 1 only; reported in the same JSON line under "configs")
+# ------------------------------------------------------------------------------------------------------
+def run_other_configs(device, peak_tflops, hbm_gbs):
+    """cfg 2-5 of BASELINE.json at full size, inputs resident in HBM, best of 3 kernel launches each (CUDA events
+    on the launching stream).  flops/step follow DESIGN.md section 3."""
+    import cases
+    from assimulo_b200.gpu import _core
+    out = []
+
+    def run(name, model, solver, y0, p, sw0, tf, flops, t_grid=None, reverse=False, **opts):
+        h = _core.Handle(device)
+        h.set_model_builtin(model)
+        h.set_ensemble(y0, p, sw0, 0.0)
+        d = {"solver": _core.SOLVER_IDS[solver]}
+        d.update(opts)
+        h.set_opts(d)
+        h.set_output(t_grid, 16)
+        h.set_fetch_reverse(reverse)
+        ms = []
+        for _ in range(4):
+            h.reset()
+            h.simulate(tf)
+            ms.append(h.last_kernel_ms())
+        ms = min(ms[1:])
+        sums, nbad = h.get_summary()
+        n = y0.shape[1]
+        rec = {"name": name, "members": int(y0.shape[0]), "model": model, "solver": solver, "kernel_ms": ms,
+               "accepted_steps": int(sums["nsteps"]), "value": sums["nsteps"] / (ms * 1e-3), "unit": UNIT,
+               "not_complete": int(nbad), "state_events": int(sums["nstateevents"]),
+               "flops_per_accepted_step": flops,
+               "fp64_frac": sums["nsteps"] * flops / (ms * 1e-3) / 1e12 / peak_tflops}
+        if t_grid is not None:
+            nbytes = float(len(t_grid)) * n * 8 * y0.shape[0]
+            rec["dense_bytes"] = nbytes
+            rec["hbm_write_frac"] = nbytes / (ms * 1e-3) / 1e9 / hbm_gbs
+        h.close()
+        out.append(rec)
+
+    N = 1 << 20
+    y0, mu = cases.vdp_sweep(N)
+    run("cfg2 RungeKutta4 h=1e-3 (strict arithmetic, bit-exact vs reference)", "vdp", "RungeKutta4", y0, mu, None, 2.0,
+        15 * 2 + 4 * 5 + 7, h=1e-3, reverse=True)
+    run("cfg2 RungeKutta34 rtol=atol=1e-6", "vdp", "RungeKutta34", y0, mu, None, 2.0, 30 * 2 + 5 * 5 + 12,
+        rtol=1e-6, atol=1e-6, inith=0.01, reverse=True)
+    y0, p, sw0 = cases.ball_sweep(N)
+    run("cfg3 Dopri5 bouncing ball, state events on device", "ball", "Dopri5", y0, p, sw0, 3.0, 81 * 2 + 20,
+        rtol=1e-6, atol=1e-6)
+    y0, p = cases.robertson_sweep(1 << 18)
+    run("cfg4 Radau5ODE Robertson, analytic Jacobian", "robertson", "Radau5ODE", y0, p, None, 40.0, 1040,
+        rtol=1e-6, atol=np.array(cases.ROBERTSON_ATOL), usejac=1)
+    y0, p = cases.gyro_sweep(1 << 22)
+    run("cfg5 Dopri5 gyro (12 states), dense output every 1e-3", "gyro", "Dopri5", y0, p, None, 0.1,
+        81 * 12 + 6 * 39 + 20, t_grid=np.linspace(0.0, 0.1, 101)[1:], rtol=1e-8, atol=1e-8)
+    return out
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -331,12 +389,22 @@ def main_gpu(a, rank, world, local_rank):
             "gpu_launches": int(launches),
             "roofline": {"bound": "fp64_fma", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s",
                          "frac": achieved / peak_tflops, "traffic": None,
-                         "peak_source": "measured live on this GPU: 1 s dependent-chain DFMA kernel "
-                                        "(aens_measure_fp64_peak); MEASURED_PEAKS.json has no fp64 entry",
+                         "peak_source": "measured live on this GPU: 1 s of 8-chain DFMA in the full-rate operand "
+                                        "form (aens_measure_fp64_peak, profiles/r1_fp64_pipe.md); "
+                                        "MEASURED_PEAKS.json has no fp64 entry",
                          "kernel": "aens_dopri5_d0_vdp_x_f", "flops_per_accepted_step": FLOPS_PER_STEP,
                          "implied_sm_mhz": peak_mhz},
             "clocks": clk,
         }
+        if a.other_configs and world == 1:
+            hbm = 6457.4
+            try:
+                hbm = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+            except Exception:
+                pass
+            del sim, prob
+            h.close()
+            line["configs"] = run_other_configs(local_rank, peak_tflops, hbm)
         if a.cpu_baseline:
             v, cores, steps, wall, kind = run_cpu_reference(n_total, a.cpu_sample)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": kind,
@@ -358,6 +426,8 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=4096)
     ap.add_argument("--host-chunks", type=int, default=0, help="chunks of the e2e host pipeline (0 = library default)")
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
+    ap.add_argument("--no-other-configs", dest="other_configs", action="store_false",
+                    help="skip the BASELINE.json configs 2-5 (they run only at --gpus 1)")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3) if a.impl == "graft" else a.warmup
     rank = int(os.environ.get("RANK", "0"))
