@@ -263,6 +263,10 @@ def main_gpu(a, rank, world, local_rank):
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
+    # stdout carries exactly ONE JSON line: anything libraries print (e.g. NCCL's version banner) goes to stderr
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -410,7 +414,8 @@ def main_gpu(a, rank, world, local_rank):
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": kind,
                                     "sample": "%d members evenly spaced over the sweep, %d accepted steps in %.2f s"
                                               % (a.cpu_sample, steps, wall)}
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
     return 0
