@@ -73,6 +73,27 @@ AENS_DEV double rcp_pos(double b) {
 }
 #endif
 
+/* FAST build: divisions become multiplications with a MUFU.RCP64H seed refined by one Newton step (2^-46 relative).
+ * Everything they touch is either a norm that steers the iteration / the step size, or the LU factors of the
+ * SIMPLIFIED Newton iteration, whose accuracy only influences the convergence rate: the iteration's fixed point is
+ * defined by the right-hand-side evaluations, which stay exact fp64.  Fractional powers go through fp32 MUFU. */
+#if AENS_STRICT
+AENS_DEV double r_recip(double b) { return 1. / b; }
+AENS_DEV double r_div(double a, double b) { return a / b; }
+AENS_DEV double r_pow(double x, double e) { return pow(x, e); }
+AENS_DEV double r_sqrt(double x) { return sqrt(x); }
+#else
+AENS_DEV double r_recip(double b) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b));
+    return fma(r, fma(-b, r, 1.0), r);
+}
+AENS_DEV double r_div(double a, double b) { return a * r_recip(b); }
+AENS_DEV double r_pow(double x, double e) { return (double)fpow((float)x, (float)e); }
+AENS_DEV double r_sqrt(double x) { return (double)sqrtf((float)x); }
+#endif
+
+
 /* one member's row of a member-major array [N][K]; 16-byte accesses when the row stride allows (the host side only
  * selects this path for 16-byte aligned bases): a warp that handles 32 consecutive members then moves one contiguous
  * 32*K*8-byte block, which matters when the array lives in host memory behind PCIe */
@@ -152,6 +173,9 @@ struct Lane {
 #pragma unroll
         for (int i = 0; i < AENS_NSTATS; ++i) st[i] = 0;
         status = AENS_ST_COMPLETE;
+#if !AENS_STRICT
+        M::prep(p);
+#endif
     }
     AENS_DEV void store(const aens_args_t &a, long long idx) {
         a.t[idx] = t;
@@ -211,20 +235,20 @@ AENS_DEV int aens_locate(S &s, Lane<M> &L, double t_low, double &t_high, double 
 #pragma unroll
             for (int i = 0; i < M::NG; ++i) {
                 if ((g_low[i] > 0) != (g_high[i] > 0)) {
-                    const double gfrac = dabs(g_high[i] / (g_low[i] - g_high[i]));
+                    const double gfrac = dabs(r_div(g_high[i], g_low[i] - g_high[i]));
                     if (gfrac >= maxfrac) { maxfrac = gfrac; gh = g_high[i]; gl = g_low[i]; }
                 }
             }
             double t_mid;
             if (gh == 0 || gl == 0) t_mid = (t_low + t_high) / 2.;
-            else t_mid = t_high - (t_high - t_low) * gh / (gh - alpha * gl);
+            else t_mid = t_high - r_div((t_high - t_low) * gh, gh - alpha * gl);
             if (dabs(t_mid - t_low) < TOL / 2.) {
-                const double fracint = dabs(t_low - t_high) / TOL;
-                t_mid = t_low + (t_high - t_low) / (2. * dmin(fracint, 5.));
+                const double fracint = r_div(dabs(t_low - t_high), TOL);
+                t_mid = t_low + r_div(t_high - t_low, 2. * dmin(fracint, 5.));
             }
             if (dabs(t_mid - t_high) < TOL / 2.) {
-                const double fracint = dabs(t_low - t_high) / TOL;
-                t_mid = t_high - (t_high - t_low) / (2. * dmin(fracint, 5.));
+                const double fracint = r_div(dabs(t_low - t_high), TOL);
+                t_mid = t_high - r_div(t_high - t_low, 2. * dmin(fracint, 5.));
             }
             s.interp(t_mid, y_high);
             M::events(t_mid, y_high, L.sw, L.p, g_mid);
@@ -583,6 +607,7 @@ struct Dopri5 {
     }
 
     AENS_DEV double hinit(const aens_args_t &a) { /* HINIT with IORD=5, ITOL=1, POSNEG=+1 */
+#if AENS_STRICT
         double dnf = 0.0, dny = 0.0;
 #pragma unroll
         for (int i = 0; i < N; ++i) {
@@ -610,12 +635,39 @@ struct Dopri5 {
         const double der12 = dmax(dabs(der2), sqrt(dnf));
         double h1;
         if (der12 <= 1.0e-15) h1 = dmax(1.0e-6, dabs(hh) * 1.0e-3);
-#if AENS_STRICT
         else h1 = pow(0.01 / der12, 1.0 / 5);
-#else
-        else h1 = (double)fpow((float)(0.01 / der12), 0.2f); /* only a starting guess for the controller */
-#endif
         return dmin(dmin(100 * dabs(hh), h1), hmax);
+#else
+        /* FAST: the result is only the controller's starting guess (and HINIT runs again after every state event):
+         * reciprocal seeds instead of divisions, fp32 MUFU square roots and fifth root */
+        double dnf = 0.0, dny = 0.0, rsk[N];
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            rsk[i] = rcp_seed(fma(a.o.rtol, dabs(L.y[i]), a.o.atol[i]));
+            const double q1 = k1[i] * rsk[i], q2 = L.y[i] * rsk[i];
+            dnf = fma(q1, q1, dnf);
+            dny = fma(q2, q2, dny);
+        }
+        double hh;
+        if (dnf <= 1.0e-10 || dny <= 1.0e-10) hh = 1.0e-6;
+        else hh = (double)(sqrtf((float)(dny * rcp_seed(dnf))) * 0.01f);
+        hh = dmin(hh, hmax);
+        double y1[N], f1[N];
+#pragma unroll
+        for (int i = 0; i < N; ++i) y1[i] = fma(hh, k1[i], L.y[i]);
+        L.rhs(L.t + hh, y1, f1);
+        double der2 = 0.0;
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            const double q = (f1[i] - k1[i]) * rsk[i];
+            der2 = fma(q, q, der2);
+        }
+        const double der12 = dmax(r_sqrt(der2) * rcp_seed(hh), r_sqrt(dnf));
+        double h1;
+        if (der12 <= 1.0e-15) h1 = dmax(1.0e-6, dabs(hh) * 1.0e-3);
+        else h1 = (double)fpow((float)(0.01 * rcp_seed(der12)), 0.2f);
+        return dmin(dmin(100 * dabs(hh), h1), hmax);
+#endif
     }
 
 #if !AENS_STRICT

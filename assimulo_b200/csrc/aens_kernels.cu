@@ -16,19 +16,36 @@
 #endif
 #define KN(base) AENS_CAT(AENS_CAT(AENS_CAT(base, AENS_KNAME), _), AENS_CAT(x, AENS_SUF))
 
+/* minimum resident CTAs per SM requested from ptxas (__launch_bounds__), per solver; tuned in profiles/ */
+#ifndef AENS_MB_EULER
+#define AENS_MB_EULER 1
+#endif
+#ifndef AENS_MB_RK4
+#define AENS_MB_RK4 1
+#endif
+#ifndef AENS_MB_RK34
+#define AENS_MB_RK34 1
+#endif
+#ifndef AENS_MB_DOPRI5
+#define AENS_MB_DOPRI5 1
+#endif
+#ifndef AENS_MB_RADAU5
+#define AENS_MB_RADAU5 1
+#endif
+
 typedef AENS_KMODEL KM;
 constexpr bool kEvents = (KM::NG > 0);
 
-AENS_DEFINE_KERNEL(KN(aens_euler_d1_), Euler, KM, true, 1)
-AENS_DEFINE_KERNEL(KN(aens_rk4_d0_), RK4, KM, false, 1)
-AENS_DEFINE_KERNEL(KN(aens_rk34_d1_), RK34, KM, true, 1)
-AENS_DEFINE_KERNEL(KN(aens_dopri5_d1_), Dopri5, KM, true, 1)
-AENS_DEFINE_KERNEL(KN(aens_radau5_d1_), Radau5, KM, true, 1)
+AENS_DEFINE_KERNEL(KN(aens_euler_d1_), Euler, KM, true, AENS_MB_EULER)
+AENS_DEFINE_KERNEL(KN(aens_rk4_d0_), RK4, KM, false, AENS_MB_RK4)
+AENS_DEFINE_KERNEL(KN(aens_rk34_d1_), RK34, KM, true, AENS_MB_RK34)
+AENS_DEFINE_KERNEL(KN(aens_dopri5_d1_), Dopri5, KM, true, AENS_MB_DOPRI5)
+AENS_DEFINE_KERNEL(KN(aens_radau5_d1_), Radau5, KM, true, AENS_MB_RADAU5)
 /* models without events additionally get dense-free variants (no interpolation data kept in registers) */
-AENS_DEFINE_KERNEL(KN(aens_euler_d0_), Euler, KM, kEvents, 1)
-AENS_DEFINE_KERNEL(KN(aens_rk34_d0_), RK34, KM, kEvents, 1)
-AENS_DEFINE_KERNEL(KN(aens_dopri5_d0_), Dopri5, KM, kEvents, 1)
-AENS_DEFINE_KERNEL(KN(aens_radau5_d0_), Radau5, KM, kEvents, 1)
+AENS_DEFINE_KERNEL(KN(aens_euler_d0_), Euler, KM, kEvents, AENS_MB_EULER)
+AENS_DEFINE_KERNEL(KN(aens_rk34_d0_), RK34, KM, kEvents, AENS_MB_RK34)
+AENS_DEFINE_KERNEL(KN(aens_dopri5_d0_), Dopri5, KM, kEvents, AENS_MB_DOPRI5)
+AENS_DEFINE_KERNEL(KN(aens_radau5_d0_), Radau5, KM, kEvents, AENS_MB_RADAU5)
 
 extern "C" const void *AENS_CAT(AENS_CAT(aens_kernels_, AENS_KNAME), AENS_SUF)(int solver, int dense) {
     switch (solver) {

@@ -17,6 +17,8 @@
  *   void jac(t, y, sw, p, double* J)            column-major J[i + j*N] = d f_i / d y_j
  *   void events(t, y, sw, p, double* g);
  *   int  handle_event(double t, double* y, unsigned char* sw, const int* event_info, const double* p);
+ *   void prep(double* p)   called once per member on its private copy of the parameters, FAST build only: a model
+ *                          may replace a divisor by its reciprocal so that rhs multiplies (AensGyro)
  * The operation order inside each rhs is the order of the Python model, so that the STRICT build reproduces the
  * reference's floating-point results bit for bit.
  */
@@ -26,6 +28,7 @@
 #define AENS_DEV __device__ __forceinline__
 
 struct AensVdp {
+    static AENS_DEV void prep(double *) {}
     static constexpr int N = 2, NP = 1, NG = 0, NSW = 0;
     static constexpr bool HAS_JAC = true;
     static AENS_DEV void rhs(double, const double *y, const unsigned char *, const double *p, double *yd) {
@@ -43,6 +46,7 @@ struct AensVdp {
 };
 
 struct AensBall {
+    static AENS_DEV void prep(double *) {}
     static constexpr int N = 2, NP = 2, NG = 2, NSW = 2;
     static constexpr bool HAS_JAC = false;
     static AENS_DEV void rhs(double, const double *y, const unsigned char *, const double *p, double *yd) {
@@ -64,6 +68,7 @@ struct AensBall {
 };
 
 struct AensRobertson {
+    static AENS_DEV void prep(double *) {}
     static constexpr int N = 3, NP = 3, NG = 0, NSW = 0;
     static constexpr bool HAS_JAC = true;
     static AENS_DEV void rhs(double, const double *y, const unsigned char *, const double *p, double *yd) {
@@ -85,8 +90,17 @@ struct AensRobertson {
 struct AensGyro {
     static constexpr int N = 12, NP = 3, NG = 0, NSW = 0;
     static constexpr bool HAS_JAC = false;
+#if defined(AENS_STRICT) && AENS_STRICT
+    static AENS_DEV void prep(double *) {}
+#else
+    static AENS_DEV void prep(double *p) { p[0] = 1.0 / p[0]; p[1] = 1.0 / p[1]; p[2] = 1.0 / p[2]; }
+#endif
     static AENS_DEV void rhs(double, const double *u, const unsigned char *, const double *p, double *ud) {
-        const double om0 = u[0] / p[0], om1 = u[1] / p[1], om2 = u[2] / p[2];
+#if defined(AENS_STRICT) && AENS_STRICT
+        const double om0 = u[0] / p[0], om1 = u[1] / p[1], om2 = u[2] / p[2]; /* omega = pi / I as in the reference */
+#else
+        const double om0 = u[0] * p[0], om1 = u[1] * p[1], om2 = u[2] * p[2]; /* p = 1/I after prep() */
+#endif
         ud[0] = om2 * u[1] + (-om1) * u[2];
         ud[1] = (-om2) * u[0] + om0 * u[2];
         ud[2] = om1 * u[0] + (-om0) * u[1];
@@ -104,6 +118,7 @@ struct AensGyro {
 };
 
 struct AensLinear {
+    static AENS_DEV void prep(double *) {}
     static constexpr int N = 1, NP = 3, NG = 0, NSW = 0;
     static constexpr bool HAS_JAC = true;
     static AENS_DEV void rhs(double, const double *y, const unsigned char *, const double *p, double *yd) {
@@ -115,6 +130,7 @@ struct AensLinear {
 };
 
 struct AensLinearEv {
+    static AENS_DEV void prep(double *) {}
     static constexpr int N = 1, NP = 3, NG = 1, NSW = 1;
     static constexpr bool HAS_JAC = true;
     static AENS_DEV void rhs(double, const double *y, const unsigned char *, const double *p, double *yd) {
@@ -131,6 +147,7 @@ struct AensLinearEv {
 };
 
 struct AensExtended {
+    static AENS_DEV void prep(double *) {}
     static constexpr int N = 3, NP = 0, NG = 3, NSW = 3;
     static constexpr bool HAS_JAC = false;
     static AENS_DEV void rhs(double, const double *, const unsigned char *sw, const double *, double *yd) {
@@ -169,6 +186,7 @@ struct AensExtended {
 #ifdef AENS_USER_MODEL
 /* NVRTC path: the user source defines the plain functions; dimensions arrive as -D macros. */
 struct AensUser {
+    static AENS_DEV void prep(double *) {}
     static constexpr int N = AENS_USER_N, NP = AENS_USER_NP, NG = AENS_USER_NG, NSW = AENS_USER_NSW;
     static constexpr bool HAS_JAC = (AENS_USER_HAS_JAC != 0);
     static AENS_DEV void rhs(double t, const double *y, const unsigned char *sw, const double *p, double *yd) {
