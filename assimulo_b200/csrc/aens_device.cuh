@@ -45,6 +45,9 @@
 namespace aens {
 
 AENS_DEV double dabs(double x) { return fabs(x); }
+/* g > 0 for the event indicators, on the bit pattern: positive non-zero doubles are exactly the positive 64-bit
+ * integers (keeps the locator's sign tests off the fp64 pipe; differs from `g > 0.` only for NaN) */
+AENS_DEV bool is_pos(double g) { return __double_as_longlong(g) > 0; }
 AENS_DEV double dmax(double a, double b) { return a >= b ? a : b; } /* Fortran MAX / radau_max / fmax on non-NaN */
 AENS_DEV double dmin(double a, double b) { return a <= b ? a : b; }
 
@@ -220,7 +223,7 @@ AENS_DEV int aens_locate(S &s, Lane<M> &L, double t_low, double &t_high, double 
     L.st[AENS_STAT_NSTATEFCNS] += 1;
     bool ev = false;
 #pragma unroll
-    for (int i = 0; i < M::NG; ++i) ev = ev || ((g_low[i] > 0) != (g_high[i] > 0));
+    for (int i = 0; i < M::NG; ++i) ev = ev || (is_pos(g_low[i]) != is_pos(g_high[i]));
     if (ev) {
         int side = 0, sideprev = -1;
         double alpha = 1.;
@@ -234,7 +237,7 @@ AENS_DEV int aens_locate(S &s, Lane<M> &L, double t_low, double &t_high, double 
             double maxfrac = 0., gh = g_high[0], gl = g_low[0];
 #pragma unroll
             for (int i = 0; i < M::NG; ++i) {
-                if ((g_low[i] > 0) != (g_high[i] > 0)) {
+                if (is_pos(g_low[i]) != is_pos(g_high[i])) {
                     const double gfrac = dabs(r_div(g_high[i], g_low[i] - g_high[i]));
                     if (gfrac >= maxfrac) { maxfrac = gfrac; gh = g_high[i]; gl = g_low[i]; }
                 }
@@ -256,7 +259,7 @@ AENS_DEV int aens_locate(S &s, Lane<M> &L, double t_low, double &t_high, double 
             sideprev = side;
             bool left = false;
 #pragma unroll
-            for (int i = 0; i < M::NG; ++i) left = left || ((g_low[i] > 0) != (g_mid[i] > 0));
+            for (int i = 0; i < M::NG; ++i) left = left || (is_pos(g_low[i]) != is_pos(g_mid[i]));
             if (left) {
                 t_high = t_mid;
 #pragma unroll
@@ -273,7 +276,7 @@ AENS_DEV int aens_locate(S &s, Lane<M> &L, double t_low, double &t_high, double 
 #pragma unroll
         for (int i = 0; i < M::NG; ++i) {
             L.event_info[i] = 0;
-            if ((g_low[i] > 0) != (g_high[i] > 0)) L.event_info[i] = (g_high[i] > 0) ? 1 : -1;
+            if (is_pos(g_low[i]) != is_pos(g_high[i])) L.event_info[i] = is_pos(g_high[i]) ? 1 : -1;
         }
         L.st[AENS_STAT_NSTATEEVENTS] += 1;
     }
@@ -590,7 +593,11 @@ struct Dopri5 {
 
     AENS_DEV void interp(double x, double *out) { /* CONTD5 */
         if (DENSE) {
+#if AENS_STRICT
             const double th = (x - told) / hstep, th1 = 1.0 - th;
+#else
+            const double th = (x - told) * hstep, th1 = 1.0 - th; /* FAST: hstep holds 1/h (set once per accepted step) */
+#endif
 #pragma unroll
             for (int i = 0; i < N; ++i)
                 out[i] = cont[i] + th * (cont[N + i] + th1 * (cont[2 * N + i] + th * (cont[3 * N + i] + th1 * cont[4 * N + i])));
@@ -1014,7 +1021,7 @@ struct Dopri5 {
                         cont[4 * N + i] = D[i];
                     }
                     told = x;
-                    hstep = h_step;
+                    hstep = r_recip(h_step);
                 }
 #pragma unroll
                 for (int i = 0; i < N; ++i) {
