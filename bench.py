@@ -37,6 +37,21 @@ RTOL = ATOL = 1e-6
 FLOPS_PER_STEP = 63 * 2 + 6 * 5 + 20
 
 
+def ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the headline kernel, from the committed ncu
+    capture of this same command (profiles/r*_ncu.json, written by tools/profile_summary.py); None if absent."""
+    import glob
+    best = None
+    for f in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu.json"))):
+        try:
+            m = json.load(open(f)).get("dopri5_vdp")
+            if m:
+                best = (m["dram__bytes_read.sum"] + m["dram__bytes_write.sum"], os.path.basename(f))
+        except Exception:
+            pass
+    return best
+
+
 def vdp_members(n_total, rank, world, per_rank):
     """Members of this rank: 32-member chunks of the global sweep dealt round-robin."""
     chunks = np.arange(rank, n_total // 32, world)[: per_rank // 32]
@@ -392,7 +407,11 @@ def main_gpu(a, rank, world, local_rank):
                             "pinned host y0/p in, pinned host y out, chunk-pipelined H2D / kernels / D2H"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "fp64_fma", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s",
-                         "frac": achieved / peak_tflops, "traffic": None,
+                         "frac": achieved / peak_tflops,
+                         "traffic": (ncu_traffic() or (None, None))[0] if a.members == (1 << 23) else None,
+                         "traffic_source": "dram bytes read+written by one launch at 2^23 members, ncu --set full, "
+                                           "profiles/%s" % (ncu_traffic() or (None, "absent"))[1],
+                         "algorithmic_bytes": a.members * ((2 * 2 + 1 + 1 + 1) * 8 + 4 + 9 * 4),
                          "peak_source": "measured live on this GPU: 1 s of 8-chain DFMA in the full-rate operand "
                                         "form (aens_measure_fp64_peak, profiles/r1_fp64_pipe.md); "
                                         "MEASURED_PEAKS.json has no fp64 entry",
