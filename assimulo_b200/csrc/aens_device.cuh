@@ -143,6 +143,13 @@ struct Lane {
     int st[AENS_NSTATS];
     int gi;      /* next dense-output row */
     int status;
+    double tnext; /* models with time events: end of the current segment = min(next time event, tfinal) */
+
+    /* the time integrate() runs to (tevent of Explicit_ODE._simulate, src/explicit_ode.pyx:212-222) */
+    AENS_DEV double tend(const aens_args_t &a) const {
+        if constexpr (M::HAS_TE) return tnext;
+        else return a.tf;
+    }
 
     AENS_DEV void rhs(double tt, const double *yy, double *yd) { M::rhs(tt, yy, sw, p, yd); }
 
@@ -348,7 +355,7 @@ struct Euler {
         }
     }
     AENS_DEV void seg_init(const aens_args_t &a, long long) {
-        h = dmin(a.o.h, dabs(a.tf - L.t));
+        h = dmin(a.o.h, dabs(L.tend(a) - L.t));
         seg_init_events(L);
         pending = (inith != 0);
     }
@@ -375,19 +382,19 @@ struct Euler {
             pending = false;
             if (flag == AENS_R_EVENT) inith = inith - (L.t - told);
             else inith = 0;
-            h = dmin(h, dabs(a.tf - L.t));
+            h = dmin(h, dabs(L.tend(a) - L.t));
             if (flag == AENS_R_EVENT && inith == 0) { /* euler.pyx:629-632 */
                 inith = h - (L.t - told);
                 if (!(dabs(inith) > 1e-15)) inith = 0.0;
             }
             return flag;
         }
-        const bool inner = (L.t + h < a.tf);
+        const bool inner = (L.t + h < L.tend(a));
         const double hs = h;
         step(hs);
         const double tn = told + hs;
         int flag = aens_post_step<M, Euler>(*this, L, a, idx, tn - hs, tn);
-        if (inner) h = dmin(h, dabs(a.tf - L.t));
+        if (inner) h = dmin(h, dabs(L.tend(a) - L.t));
         if (flag == AENS_R_EVENT) {
             if (inith == 0) { /* euler.pyx:629-632 */
                 inith = h - (L.t - told);
@@ -412,9 +419,9 @@ struct RK4 {
     AENS_DEV void load_aux(const aens_args_t &, long long) {}
     AENS_DEV void store_aux(const aens_args_t &, long long) {}
     AENS_DEV void interp(double, double *) {}
-    AENS_DEV void seg_init(const aens_args_t &a, long long) { h = dmin(a.o.h, dabs(a.tf - L.t)); }
+    AENS_DEV void seg_init(const aens_args_t &a, long long) { h = dmin(a.o.h, dabs(L.tend(a) - L.t)); }
     AENS_DEV int attempt(const aens_args_t &a, long long) {
-        const bool inner = (L.t + h < a.tf);
+        const bool inner = (L.t + h < L.tend(a));
         double Y1[N], Y2[N], Y3[N], Y4[N], arg[N];
         const double t = L.t;
         L.rhs(t, L.y, Y1);
@@ -434,7 +441,7 @@ struct RK4 {
         L.st[AENS_STAT_NFCNS] += 4;
         L.st[AENS_STAT_NSTEPS] += 1;
         L.st[AENS_STAT_NSTEPSTOTAL] += 1;
-        if (inner) { h = dmin(h, dabs(a.tf - L.t)); return AENS_R_CONTINUE; }
+        if (inner) { h = dmin(h, dabs(L.tend(a) - L.t)); return AENS_R_CONTINUE; }
         return AENS_R_COMPLETE;
     }
 };
@@ -467,12 +474,12 @@ struct RK34 {
     }
     AENS_DEV void seg_init(const aens_args_t &a, long long) {
         seg_init_events(L);
-        h = dmin(a.o.inith, dabs(a.tf - L.t));
+        h = dmin(a.o.inith, dabs(L.tend(a) - L.t));
         L.rhs(L.t, L.y, Y1);
         it = 0;
     }
     AENS_DEV int attempt(const aens_args_t &a, long long idx) {
-        const bool inner = (L.t + h < a.tf);
+        const bool inner = (L.t + h < L.tend(a));
         if (it >= a.o.maxsteps) { /* for-else: 'Final time not reached within maximum number of steps' */
             L.status = AENS_ST_MAXSTEPS;
             return AENS_R_ERROR;
@@ -530,7 +537,7 @@ struct RK34 {
             if (!(err2 > 0.0)) fac = 2.0;
 #endif
             h = h * fac;
-            h = dmin(h, dabs(a.tf - L.t));
+            h = dmin(h, dabs(L.tend(a) - L.t));
             it += 1;
         }
         if (flag == AENS_R_EVENT) return AENS_R_EVENT;
@@ -687,7 +694,7 @@ struct Dopri5 {
     struct Bounds { double rem, b101; };
     AENS_DEV Bounds next_bounds(const aens_args_t &a, double xn) const {
         Bounds b;
-        b.rem = a.tf - xn;
+        b.rem = L.tend(a) - xn;
         b.b101 = b.rem * (1.0 / 1.01);
         return b;
     }
@@ -714,7 +721,7 @@ struct Dopri5 {
 
     AENS_DEV void seg_init(const aens_args_t &a, long long idx) {
         seg_init_events(L);
-        hmax = dabs((a.o.maxh == 0.0) ? (a.tf - L.t) : a.o.maxh); /* dopri5.f:301-305, :392 */
+        hmax = dabs((a.o.maxh == 0.0) ? (L.tend(a) - L.t) : a.o.maxh); /* dopri5.f:301-305, :392 */
 #if AENS_STRICT
         facold = 1.0e-4;
 #else
@@ -760,7 +767,7 @@ struct Dopri5 {
         if (nstep > a.o.maxsteps) { L.status = AENS_ST_MAXSTEPS; return AENS_R_ERROR; }
         const double x = L.t;
         if (0.1 * dabs(h) <= dabs(x) * uround) { L.status = AENS_ST_STEP_TOO_SMALL; return AENS_R_ERROR; }
-        if ((x + 1.01 * h - a.tf) > 0.0) { h = a.tf - x; last = true; }
+        if ((x + 1.01 * h - L.tend(a)) > 0.0) { h = L.tend(a) - x; last = true; }
         nstep += 1;
         double k2[N], k3[N], k4[N], k5[N], k6[N], y1[N];
 #pragma unroll
@@ -862,7 +869,10 @@ struct Dopri5 {
             return AENS_R_ERROR;
         }
         nstep += 1;
-        const double xph = x + h;
+        /* the last step lands on the end point exactly: x + (xend - x) can miss xend by an ulp, which the
+         * reference tolerates at tfinal (100 eps slack of the driver loop) but not at a time event, where the next
+         * segment would then be one ulp long */
+        const double xph = last ? L.tend(a) : x + h;
         const Bounds nb = next_bounds(a, xph);
         double y1[N], k2[N], E[N], hk1[N], hk7[DENSE ? N : 1], D[DENSE ? N : 1];
         if constexpr (INCREMENTAL) {
@@ -1057,6 +1067,7 @@ __device__ __forceinline__ void aens_run(const aens_args_t &a) {
     S s;
     long long idx = -1;
     int phase = PH_IDLE;
+    bool te_at_end = false; /* models with time events: the current segment ends on a time event */
     bool pending = false; /* a finished member waits in this lane's registers for the warp's next common store point */
     bool drained = false; /* warp-uniform: the queue has no more members */
     for (;;) {
@@ -1090,6 +1101,11 @@ __device__ __forceinline__ void aens_run(const aens_args_t &a) {
             if (a.q_begin + (long long)base + nidle >= a.q_end) drained = true;
         }
         if (phase == PH_SEGINIT) {
+            if constexpr (M::HAS_TE) { /* tevent = min(time_events(t, y, sw), tfinal), explicit_ode.pyx:212-216 */
+                const double tret = M::time_events(s.L.t, s.L.y, s.L.sw, s.L.p);
+                s.L.tnext = (tret < a.tf) ? tret : a.tf;
+                te_at_end = (tret == s.L.tnext); /* a time event falls on the end of this segment */
+            }
             s.seg_init(a, idx);
             phase = PH_STEP;
         }
@@ -1105,7 +1121,7 @@ __device__ __forceinline__ void aens_run(const aens_args_t &a) {
                 bool done = true;
                 if (r == AENS_R_EVENT) {
                     /* explicit_ode.pyx:233-264: log, handle_event, restart the solver (initialize=True) */
-                    const int ne = s.L.st[AENS_STAT_NSTATEEVENTS] - 1;
+                    const int ne = s.L.st[AENS_STAT_NSTATEEVENTS] + s.L.st[AENS_STAT_NTIMEEVENTS] - 1;
                     if (a.ev_slots > 0) {
                         int mask = 0;
 #pragma unroll
@@ -1124,7 +1140,21 @@ __device__ __forceinline__ void aens_run(const aens_args_t &a) {
                         done = false;
                     }
                 } else if (r == AENS_R_COMPLETE) {
-                    if (s.L.t != a.tf && s.L.t + eps * aens::dmax(aens::dabs(s.L.t), aens::dabs(a.tf)) < a.tf) {
+                    if constexpr (M::HAS_TE) {
+                        /* explicit_ode.pyx:233-264 with flag == ID_COMPLETE: (tevent != tfinal) or (tret == tevent) */
+                        if (s.L.tnext != a.tf || te_at_end) {
+                            s.L.st[AENS_STAT_NTIMEEVENTS] += 1;
+                            if (a.ev_slots > 0) {
+                                const int ne = s.L.st[AENS_STAT_NSTATEEVENTS] + s.L.st[AENS_STAT_NTIMEEVENTS] - 1;
+                                const long long slot = (long long)(ne % a.ev_slots) * a.N + idx;
+                                a.ev_t[slot] = s.L.t;
+                                a.ev_info[slot] = 1 << 30;
+                            }
+                            if (M::handle_time_event(s.L.t, s.L.y, s.L.sw, s.L.p)) s.L.status = AENS_ST_TERMINATED;
+                        }
+                    }
+                    if (s.L.status != AENS_ST_TERMINATED && s.L.t != a.tf &&
+                        s.L.t + eps * aens::dmax(aens::dabs(s.L.t), aens::dabs(a.tf)) < a.tf) {
                         phase = PH_SEGINIT; /* integrate() returned short of tfinal: the driver calls it again */
                         done = false;
                     }

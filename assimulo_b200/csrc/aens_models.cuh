@@ -10,6 +10,7 @@
  *   Linear     y' = p0*y + p1 (tests/solvers/test_rungekutta.py:40-47, examples/dopri5_basic.py)
  *   LinearEv   + g = y - p2, handle_event: sw[0] <- False  (tests/test_solvers.py:27-57)
  *   Extended   tests/conftest.py:26-114 Extended_Problem (event iteration inside handle_event)
+ *   TimeEv     tests/solvers/test_rungekutta.py:49-82 (time events + handle_event with event_info[1] = True)
  *
  * Interface of a model M (all static, all __device__):
  *   constexpr int N, NP, NG, NSW; constexpr bool HAS_JAC;
@@ -27,8 +28,17 @@
 
 #define AENS_DEV __device__ __forceinline__
 
-struct AensVdp {
+/* what a model inherits unless it says otherwise: no parameter preparation, no time events */
+struct AensModelDefaults {
+    static constexpr bool HAS_TE = false;
     static AENS_DEV void prep(double *) {}
+    static AENS_DEV double time_events(double, const double *, const unsigned char *, const double *) {
+        return AENS_NO_TIME_EVENT;
+    }
+    static AENS_DEV int handle_time_event(double, double *, unsigned char *, const double *) { return 0; }
+};
+
+struct AensVdp : AensModelDefaults {
     static constexpr int N = 2, NP = 1, NG = 0, NSW = 0;
     static constexpr bool HAS_JAC = true;
     static AENS_DEV void rhs(double, const double *y, const unsigned char *, const double *p, double *yd) {
@@ -45,8 +55,7 @@ struct AensVdp {
     static AENS_DEV int handle_event(double, double *, unsigned char *, const int *, const double *) { return 0; }
 };
 
-struct AensBall {
-    static AENS_DEV void prep(double *) {}
+struct AensBall : AensModelDefaults {
     static constexpr int N = 2, NP = 2, NG = 2, NSW = 2;
     static constexpr bool HAS_JAC = false;
     static AENS_DEV void rhs(double, const double *y, const unsigned char *, const double *p, double *yd) {
@@ -67,8 +76,7 @@ struct AensBall {
     }
 };
 
-struct AensRobertson {
-    static AENS_DEV void prep(double *) {}
+struct AensRobertson : AensModelDefaults {
     static constexpr int N = 3, NP = 3, NG = 0, NSW = 0;
     static constexpr bool HAS_JAC = true;
     static AENS_DEV void rhs(double, const double *y, const unsigned char *, const double *p, double *yd) {
@@ -87,12 +95,10 @@ struct AensRobertson {
     static AENS_DEV int handle_event(double, double *, unsigned char *, const int *, const double *) { return 0; }
 };
 
-struct AensGyro {
+struct AensGyro : AensModelDefaults {
     static constexpr int N = 12, NP = 3, NG = 0, NSW = 0;
     static constexpr bool HAS_JAC = false;
-#if defined(AENS_STRICT) && AENS_STRICT
-    static AENS_DEV void prep(double *) {}
-#else
+#if !(defined(AENS_STRICT) && AENS_STRICT)
     static AENS_DEV void prep(double *p) { p[0] = 1.0 / p[0]; p[1] = 1.0 / p[1]; p[2] = 1.0 / p[2]; }
 #endif
     static AENS_DEV void rhs(double, const double *u, const unsigned char *, const double *p, double *ud) {
@@ -117,8 +123,7 @@ struct AensGyro {
     static AENS_DEV int handle_event(double, double *, unsigned char *, const int *, const double *) { return 0; }
 };
 
-struct AensLinear {
-    static AENS_DEV void prep(double *) {}
+struct AensLinear : AensModelDefaults {
     static constexpr int N = 1, NP = 3, NG = 0, NSW = 0;
     static constexpr bool HAS_JAC = true;
     static AENS_DEV void rhs(double, const double *y, const unsigned char *, const double *p, double *yd) {
@@ -129,8 +134,7 @@ struct AensLinear {
     static AENS_DEV int handle_event(double, double *, unsigned char *, const int *, const double *) { return 0; }
 };
 
-struct AensLinearEv {
-    static AENS_DEV void prep(double *) {}
+struct AensLinearEv : AensModelDefaults {
     static constexpr int N = 1, NP = 3, NG = 1, NSW = 1;
     static constexpr bool HAS_JAC = true;
     static AENS_DEV void rhs(double, const double *y, const unsigned char *, const double *p, double *yd) {
@@ -146,8 +150,7 @@ struct AensLinearEv {
     }
 };
 
-struct AensExtended {
-    static AENS_DEV void prep(double *) {}
+struct AensExtended : AensModelDefaults {
     static constexpr int N = 3, NP = 0, NG = 3, NSW = 3;
     static constexpr bool HAS_JAC = false;
     static AENS_DEV void rhs(double, const double *, const unsigned char *sw, const double *, double *yd) {
@@ -183,10 +186,43 @@ struct AensExtended {
     }
 };
 
+/* tests/solvers/test_rungekutta.py:49-82 test_time_event: y' = p5, time events at p0 < p1 < p2 < p3, handle_event:
+ * y += p4 */
+struct AensTimeEv : AensModelDefaults {
+    static constexpr int N = 1, NP = 6, NG = 0, NSW = 0;
+    static constexpr bool HAS_JAC = true;
+    static constexpr bool HAS_TE = true;
+    static AENS_DEV void rhs(double, const double *, const unsigned char *, const double *p, double *yd) { yd[0] = p[5]; }
+    static AENS_DEV void jac(double, const double *, const unsigned char *, const double *, double *J) { J[0] = 0.; }
+    static AENS_DEV void events(double, const double *, const unsigned char *, const double *, double *) {}
+    static AENS_DEV int handle_event(double, double *, unsigned char *, const int *, const double *) { return 0; }
+    static AENS_DEV double time_events(double t, const double *, const unsigned char *, const double *p) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (t < p[k]) return p[k];
+        return AENS_NO_TIME_EVENT;
+    }
+    static AENS_DEV int handle_time_event(double, double *y, unsigned char *, const double *p) {
+        y[0] += p[4];
+        return 0;
+    }
+};
+
 #ifdef AENS_USER_MODEL
 /* NVRTC path: the user source defines the plain functions; dimensions arrive as -D macros. */
-struct AensUser {
-    static AENS_DEV void prep(double *) {}
+#ifndef AENS_USER_HAS_TE
+#define AENS_USER_HAS_TE 0
+#endif
+struct AensUser : AensModelDefaults {
+    static constexpr bool HAS_TE = (AENS_USER_HAS_TE != 0);
+#if AENS_USER_HAS_TE
+    static AENS_DEV double time_events(double t, const double *y, const unsigned char *sw, const double *p) {
+        return aens_time_events(t, y, sw, p);
+    }
+    static AENS_DEV int handle_time_event(double t, double *y, unsigned char *sw, const double *p) {
+        return aens_handle_time_event(t, y, sw, p);
+    }
+#endif
     static constexpr int N = AENS_USER_N, NP = AENS_USER_NP, NG = AENS_USER_NG, NSW = AENS_USER_NSW;
     static constexpr bool HAS_JAC = (AENS_USER_HAS_JAC != 0);
     static AENS_DEV void rhs(double t, const double *y, const unsigned char *sw, const double *p, double *yd) {

@@ -350,17 +350,17 @@ struct Radau5 {
         /* radau5_solve, radau5.c:192-216 */
         rtol1 = pow(a.o.rtol, rd::expm) * .1;
         const double x = L.t;
-        const double hmax = (a.o.maxh != 0.0) ? a.o.maxh : a.tf - x;
+        const double hmax = (a.o.maxh != 0.0) ? a.o.maxh : L.tend(a) - x;
         if (a.o.fnewt != 0.0) fnewt = a.o.fnewt;
         else fnewt = dmax(rd::uround * 10 / rtol1, dmin(.03, pow(rtol1, .5)));
         /* _radcor prologue, radau5.c:327-363 (posneg = +1) */
         h = a.o.inith;
-        hmaxn = dmin(dabs(hmax), dabs(a.tf - x));
+        hmaxn = dmin(dabs(hmax), dabs(L.tend(a) - x));
         if (dabs(h) <= rd::uround * 10.) h = 1e-6;
         h = dmin(dabs(h), hmaxn);
         hold = h;
         reject = false; first = true; last = false;
-        if ((x + h * 1.0001 - a.tf) >= 0.) { h = a.tf - x; last = true; }
+        if ((x + h * 1.0001 - L.tend(a)) >= 0.) { h = L.tend(a) - x; last = true; }
         cfac = a.o.safe * ((a.o.newt << 1) + 1);
         nsing = 0; naccpt = 0; nsteps = 0;
 #if !AENS_STRICT
@@ -626,7 +626,7 @@ struct Radau5 {
             }
 #pragma unroll(N <= 4 ? 64 : 1)
             for (int i = 0; i < N; ++i) scal[i] = make_scal(a, i);
-            if (dabs(a.tf - xph) < 100 * uround * dabs(xph)) { xn = a.tf; last = true; }
+            if (dabs(L.tend(a) - xph) < 100 * uround * dabs(xph)) { xn = L.tend(a); last = true; }
             xsol = xn;
 #pragma unroll(N <= 4 ? 64 : 1)
             for (int i = 0; i < N; ++i) cont[i] = L.y[i];
@@ -640,8 +640,8 @@ struct Radau5 {
             hnew = dmin(dabs(hnew), hmaxn);
             if (reject) hnew = dmin(dabs(hnew), dabs(h));
             reject = false;
-            if ((xn + r_div(hnew, a.o.quot1) - a.tf) >= 0.) {
-                h = a.tf - xn;
+            if ((xn + r_div(hnew, a.o.quot1) - L.tend(a)) >= 0.) {
+                h = L.tend(a) - xn;
                 last = true;
             } else {
                 const double qt = r_div(hnew, h);

@@ -76,7 +76,9 @@ cdef extern from "assimulo_cuda.h":
     int aens_get_summary(aens_handle_t *h, long long *sums, long long *n_not_complete) nogil
     int aens_set_host_mode(aens_handle_t *h, int mode) nogil
 
-STAT_NAMES = ("nsteps", "nfcns", "nerrfails", "njacs", "nlus", "nstatefcns", "nstateevents", "nstepstotal")
+STAT_NAMES = ("nsteps", "nfcns", "nerrfails", "njacs", "nlus", "nstatefcns", "nstateevents", "nstepstotal",
+              "ntimeevents")
+MODEL_HAS_JAC, MODEL_TIME_EVENTS = 1, 2
 SOLVER_IDS = {"ExplicitEuler": 0, "RungeKutta4": 1, "RungeKutta34": 2, "Dopri5": 3, "Radau5ODE": 4}
 MAX_N = 16
 
@@ -107,7 +109,7 @@ cdef dict _opts_to_dict(aens_opts_t *o):
                 fac1=o.fac1, fac2=o.fac2, beta=o.beta, thet=o.thet, fnewt=o.fnewt, quot1=o.quot1, quot2=o.quot2)
 
 
-def nvrtc_check(src, int n, int n_p=0, int n_g=0, int n_sw=0, bint has_jac=False, bint strict=False):
+def nvrtc_check(src, int n, int n_p=0, int n_g=0, int n_sw=0, int has_jac=0, bint strict=False):
     """Compile-only check of a CUDA model source (no GPU needed).  Returns the cubin size."""
     cdef bytes b = src.encode() if isinstance(src, str) else src
     cdef char err[4096]
@@ -204,7 +206,8 @@ cdef class Handle:
         self._check(aens_set_model_builtin(self.h, b))
         self._dims()
 
-    def set_model_source(self, src, int n, int n_p=0, int n_g=0, int n_sw=0, bint has_jac=False):
+    def set_model_source(self, src, int n, int n_p=0, int n_g=0, int n_sw=0, int has_jac=0):
+        # has_jac: 0/1 or a bit set of MODEL_HAS_JAC | MODEL_TIME_EVENTS
         cdef bytes b = src.encode() if isinstance(src, str) else src
         cdef const char *cs = b
         cdef int rc
@@ -353,7 +356,7 @@ cdef class Handle:
             assert a.dtype == np.intc and a.size == N and a.flags.c_contiguous
             sto = <int*>np.PyArray_DATA(a)
         cdef const double *yptr = &y[0, 0]
-        cdef long long sums[8]
+        cdef long long sums[9]
         cdef long long nbad = 0
         cdef int rc
         with nogil:
@@ -361,16 +364,16 @@ cdef class Handle:
         self._check(rc)
         self.N = N
         self.n_out = 0
-        return {STAT_NAMES[i]: sums[i] for i in range(8)}, nbad
+        return {STAT_NAMES[i]: sums[i] for i in range(9)}, nbad
 
     def get_summary(self):
-        cdef long long s[8]
+        cdef long long s[9]
         cdef long long nbad = 0
         cdef int rc
         with nogil:
             rc = aens_get_summary(self.h, s, &nbad)
         self._check(rc)
-        return {STAT_NAMES[i]: s[i] for i in range(8)}, nbad
+        return {STAT_NAMES[i]: s[i] for i in range(9)}, nbad
 
     def simulate_async(self, double tfinal):
         cdef int rc
@@ -435,12 +438,12 @@ cdef class Handle:
         return out
 
     def get_stats_sum(self):
-        cdef long long s[8]
+        cdef long long s[9]
         cdef int rc
         with nogil:
             rc = aens_get_stats_sum(self.h, s)
         self._check(rc)
-        return {STAT_NAMES[i]: s[i] for i in range(8)}
+        return {STAT_NAMES[i]: s[i] for i in range(9)}
 
     def get_dense(self, slot=None):
         """Row `slot` as [N,n], or all rows as [n_out,N,n] when slot is None."""
@@ -467,7 +470,7 @@ cdef class Handle:
 
     def get_events(self):
         """Returns (count[N], t_ev[N,slots], info[N,slots]) -- ring order, see assimulo_cuda.h."""
-        cdef int S = self.event_slots if (self.n_g > 0 and self.event_slots > 0) else 0
+        cdef int S = self.event_slots if ((self.n_g > 0 or (self.has_jac & 2)) and self.event_slots > 0) else 0
         cdef np.ndarray[int, ndim=1, mode="c"] cnt = np.zeros(self.N, dtype=np.intc)
         cdef np.ndarray[double, ndim=2, mode="c"] te = np.full((self.N, max(S, 1)), np.nan)
         cdef np.ndarray[int, ndim=2, mode="c"] info = np.zeros((self.N, max(S, 1)), dtype=np.intc)

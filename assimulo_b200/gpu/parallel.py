@@ -10,6 +10,8 @@ One process per GPU (torchrun); ``torch.distributed`` is plumbing only.
 """
 import numpy as np
 
+from .solvers import STAT_NAMES
+
 
 def shard_bounds(N, rank, world):
     """[lo, hi) of this rank's contiguous block and the padded block size B = ceil(N / world)."""
@@ -40,7 +42,7 @@ def shard_problem(problem, rank, world):
     if problem.model is not None:
         return Batched_Explicit_Problem(model=problem.model, **kw)
     return Batched_Explicit_Problem(source=problem.source, n=problem.n, n_p=problem.n_p, n_g=problem.n_g,
-                                    n_sw=problem.n_sw, has_jac=problem.has_jac, **kw)
+                                    n_sw=problem.n_sw, has_jac=problem.has_jac, time_events=problem.time_events, **kw)
 
 
 class _DevView(object):
@@ -71,7 +73,7 @@ def gather_final(solver, N_total, group=None):
         t_loc = view(0, (B,), "<f8")
         y_loc = view(1, (n, B), "<f8")
         st_loc = view(2, (B,), "<i4")
-        stats_loc = view(3, (8, B), "<i4")
+        stats_loc = view(3, (len(STAT_NAMES), B), "<i4")
         outs = []
         for loc in (t_loc, y_loc, st_loc, stats_loc):
             out = torch.empty((world,) + tuple(loc.shape), dtype=loc.dtype, device=dev)
@@ -83,9 +85,7 @@ def gather_final(solver, N_total, group=None):
         t_loc = torch.from_numpy(np.ascontiguousarray(solver.t_members))
         y_loc = torch.from_numpy(np.ascontiguousarray(solver.y.T))
         st_loc = torch.from_numpy(np.ascontiguousarray(solver.status.astype(np.int32)))
-        stats_loc = torch.from_numpy(np.stack([solver.statistics.per_member(k) for k in
-                                               ("nsteps", "nfcns", "nerrfails", "njacs", "nlus", "nstatefcns",
-                                                "nstateevents", "nstepstotal")]).astype(np.int32))
+        stats_loc = torch.from_numpy(np.stack([solver.statistics.per_member(k) for k in STAT_NAMES]).astype(np.int32))
         outs = []
         for loc in (t_loc, y_loc, st_loc, stats_loc):
             lst = [torch.empty_like(loc) for _ in range(world)]
@@ -102,6 +102,6 @@ def assemble(t_all, y_all, st_all, stats_all, N_total):
     y = np.transpose(y_all, (0, 2, 1)).reshape(world * B, n)[:N_total]
     status = st_all.reshape(world * B)[:N_total]
     stats = np.transpose(stats_all, (1, 0, 2)).reshape(stats_all.shape[1], world * B)[:, :N_total]
-    names = ("nsteps", "nfcns", "nerrfails", "njacs", "nlus", "nstatefcns", "nstateevents", "nstepstotal")
+    names = STAT_NAMES
     return {"t": t, "y": y, "status": status, "stats_per_member": {k: stats[i] for i, k in enumerate(names)},
             "statistics": {k: int(stats[i].astype(np.int64).sum()) for i, k in enumerate(names)}}

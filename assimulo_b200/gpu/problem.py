@@ -20,7 +20,10 @@ BUILTIN_MODELS = {
     "linear": (1, 3, 0, 0, True, [-1.0, 0.0, 0.0]),
     "linear_ev": (1, 3, 1, 1, True, [-1.0, 0.0, 0.5]),
     "extended": (3, 0, 3, 3, False, []),
+    "time_ev": (1, 6, 0, 0, True, [1.0, 2.0, 2.5, 3.0, 1.0, 1.0]),
 }
+#: built-in models that define time events (Explicit_Problem.time_events, src/explicit_ode.pyx:212-216)
+TIME_EVENT_MODELS = ("time_ev",)
 
 
 class Batched_Explicit_Problem(object):
@@ -29,8 +32,9 @@ class Batched_Explicit_Problem(object):
     Parameters::
 
         model   name of a built-in model (see BUILTIN_MODELS), or None when `source` is given
-        source  CUDA C source defining ``aens_rhs`` (and ``aens_jac``, ``aens_events``, ``aens_handle_event``
-                as announced by has_jac / n_g), see include/assimulo_cuda.h
+        source  CUDA C source defining ``aens_rhs`` (and ``aens_jac``, ``aens_events``, ``aens_handle_event``,
+                ``aens_time_events`` / ``aens_handle_time_event`` as announced by has_jac / n_g / time_events),
+                see include/assimulo_cuda.h
         y0      [N, n] initial states (a single [n] row is broadcast when p or N fixes the ensemble size)
         p0      [N, n_p] parameters (Explicit_Problem.p0)
         sw0     [N, n_sw] switches (Explicit_Problem.sw0)
@@ -39,19 +43,22 @@ class Batched_Explicit_Problem(object):
     """
 
     def __init__(self, model=None, y0=None, p0=None, sw0=None, t0=0.0, name="---", source=None, n=None, n_p=0,
-                 n_g=0, n_sw=0, has_jac=False, N=None):
+                 n_g=0, n_sw=0, has_jac=False, N=None, time_events=False):
         if (model is None) == (source is None):
             raise AssimuloException("Give exactly one of model= (built-in) or source= (CUDA C string).")
         if model is not None:
             if model not in BUILTIN_MODELS:
                 raise AssimuloException("Unknown built-in model '%s'. Available: %s" % (model, sorted(BUILTIN_MODELS)))
             n, n_p, n_g, n_sw, has_jac, pdef = BUILTIN_MODELS[model]
+            time_events = model in TIME_EVENT_MODELS
         else:
             if n is None:
                 raise AssimuloException("source= requires the state dimension n.")
             pdef = [0.0] * n_p
         self.model, self.source, self.name = model, source, name
         self.n, self.n_p, self.n_g, self.n_sw, self.has_jac = int(n), int(n_p), int(n_g), int(n_sw), bool(has_jac)
+        #: the model defines aens_time_events / aens_handle_time_event (Explicit_Problem.time_events)
+        self.time_events = bool(time_events)
         self.t0 = float(t0)
         if y0 is None:
             raise AssimuloException("y0 must be given.")

@@ -23,7 +23,8 @@ from .exception import (AssimuloException, Dopri5_Exception, Explicit_ODE_Except
 from .problem import Batched_Explicit_Problem
 
 ARITH = {"strict": 0, "fast": 1}
-STAT_NAMES = ("nsteps", "nfcns", "nerrfails", "njacs", "nlus", "nstatefcns", "nstateevents", "nstepstotal")
+STAT_NAMES = ("nsteps", "nfcns", "nerrfails", "njacs", "nlus", "nstatefcns", "nstateevents", "nstepstotal",
+              "ntimeevents")
 
 # status codes (include/assimulo_cuda.h)
 ST_COMPLETE, ST_TERMINATED = 0, 1
@@ -95,7 +96,8 @@ class Batched_Explicit_ODE(object):
                 self._handle.set_model_builtin(self.problem.model)
             else:
                 p = self.problem
-                self._handle.set_model_source(p.source, p.n, p.n_p, p.n_g, p.n_sw, p.has_jac)
+                self._handle.set_model_source(p.source, p.n, p.n_p, p.n_g, p.n_sw,
+                                              int(bool(p.has_jac)) | (2 if p.time_events else 0))
         return self._handle
 
     def _opts_dict(self):
@@ -270,10 +272,10 @@ class Batched_Explicit_ODE(object):
     @property
     def event_log(self):
         """(count[N], t_event[N, slots], info[N, slots]): ring of the last `event_slots` state events of each
-        member.  info bit 2i: indicator i fired; bit 2i+1: event_info[i] == +1 (else -1), cf.
-        src/explicit_ode.pyx:351-357."""
+        member (state and time events).  info bit 2i: indicator i fired; bit 2i+1: event_info[i] == +1 (else -1), cf.
+        src/explicit_ode.pyx:351-357; bit 30: time event."""
         if self._events is None:
-            if self._launched and self.problem.n_g > 0:
+            if self._launched and (self.problem.n_g > 0 or self.problem.time_events):
                 self._events = self._handle.get_events()
             else:
                 self._events = (np.zeros(self.N, dtype=np.intc), np.zeros((self.N, 0)),

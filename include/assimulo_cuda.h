@@ -76,7 +76,8 @@ extern "C" {
 #define AENS_STAT_NSTATEFCNS 5
 #define AENS_STAT_NSTATEEVENTS 6
 #define AENS_STAT_NSTEPSTOTAL 7      /* step attempts (DOPRI5 NSTEP, Radau nsteps) */
-#define AENS_NSTATS 8
+#define AENS_STAT_NTIMEEVENTS 8      /* time events (src/explicit_ode.pyx:241-242) */
+#define AENS_NSTATS 9
 
 /* arithmetic mode */
 #define AENS_ARITH_STRICT 0  /* reference operation order, no FMA contraction, fp64 pow/sqrt/div everywhere */
@@ -109,15 +110,24 @@ int aens_destroy(aens_handle_t **h);
 const char *aens_last_error(const aens_handle_t *h);
 const char *aens_version(void);
 
-/* Models.  Built-ins: "vdp" "ball" "robertson" "gyro" "linear" "linear_ev" "extended".
+/* Models.  Built-ins: "vdp" "ball" "robertson" "gyro" "linear" "linear_ev" "extended" "time_ev".
  * aens_set_model_source compiles `cuda_src` with NVRTC for sm_100a.  The source must define
  *   __device__ void aens_rhs(double t, const double* y, const unsigned char* sw, const double* p, double* yd);
  * and, when the corresponding flag/count says so,
  *   __device__ void aens_jac(double t, const double* y, const unsigned char* sw, const double* p, double* J_colmajor);
  *   __device__ void aens_events(double t, const double* y, const unsigned char* sw, const double* p, double* g);
  *   __device__ int  aens_handle_event(double t, double* y, unsigned char* sw, const int* event_info, const double* p);
- * (handle_event returns non-zero to terminate the member). */
+ * (handle_event returns non-zero to terminate the member), and, when `has_jac` carries the flag
+ * AENS_MODEL_TIME_EVENTS, the time-event pair of Explicit_Problem.time_events / handle_event with
+ * event_info = [[], True] (src/explicit_ode.pyx:212-216,239-259):
+ *   __device__ double aens_time_events(double t, const double* y, const unsigned char* sw, const double* p);
+ *                     next time event strictly after t, or AENS_NO_TIME_EVENT (the reference's None)
+ *   __device__ int    aens_handle_time_event(double t, double* y, unsigned char* sw, const double* p); */
+#define AENS_MODEL_HAS_JAC 1
+#define AENS_MODEL_TIME_EVENTS 2
+#define AENS_NO_TIME_EVENT (1.0e300 * 1.0e300) /* +inf */
 int aens_set_model_builtin(aens_handle_t *h, const char *name);
+/* has_jac: 0/1 as before, or a bit set of AENS_MODEL_* flags */
 int aens_set_model_source(aens_handle_t *h, const char *cuda_src, int n, int n_p, int n_g, int n_sw, int has_jac);
 int aens_model_dims(const aens_handle_t *h, int *n, int *n_p, int *n_g, int *n_sw, int *has_jac);
 
@@ -180,7 +190,8 @@ int aens_get_dense(aens_handle_t *h, int slot, double *y_out);
 int aens_get_dense_all(aens_handle_t *h, double *y_out);
 /* event log: count[N] = events seen; t_ev[N][event_slots], info[N][event_slots] hold the last
  * min(count,event_slots) events of each member in ring order (event e sits in slot e % event_slots);
- * info bit 2i = indicator i fired, bit 2i+1 = its event_info is +1 (else -1). */
+ * info bit 2i = indicator i fired, bit 2i+1 = its event_info is +1 (else -1); bit 30 = time event.  count
+ * includes time events. */
 int aens_get_events(aens_handle_t *h, int *count, double *t_ev, int *info);
 
 /* Raw device pointers (SoA, for zero-copy consumers such as an NCCL all-gather of final states):

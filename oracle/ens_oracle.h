@@ -15,7 +15,7 @@ extern "C" {
 
 enum { ORA_EULER = 0, ORA_RK4 = 1, ORA_RK34 = 2, ORA_DOPRI5 = 3, ORA_RADAU5 = 4 };
 enum { ORA_VDP = 0, ORA_BALL = 1, ORA_ROBERTSON = 2, ORA_GYRO = 3, ORA_LINEAR = 4, ORA_LINEAR_EV = 5,
-       ORA_EXTENDED = 6 };
+       ORA_EXTENDED = 6, ORA_TIME_EV = 7 };
 
 /* per-lane status */
 #define ORA_ST_COMPLETE 0
@@ -27,7 +27,7 @@ enum { ORA_VDP = 0, ORA_BALL = 1, ORA_ROBERTSON = 2, ORA_GYRO = 3, ORA_LINEAR = 
 
 /* statistics slots (names follow src/ode.pyx:153-172) */
 enum { ORA_NSTEPS = 0, ORA_NFCNS, ORA_NERRFAILS, ORA_NJACS, ORA_NLUS, ORA_NSTATEFCNS, ORA_NSTATEEVENTS,
-       ORA_NSTEPSTOTAL, ORA_NSTATS };
+       ORA_NSTEPSTOTAL, ORA_NTIMEEVENTS, ORA_NSTATS };
 
 typedef struct {
     int solver;
@@ -49,7 +49,8 @@ int  ora_model_dims(int model, int *n, int *np, int *ng, int *nsw);
 /* Simulate N independent members.  All arrays are member-major ("AoS"): y0[N][n], p[N][np], sw0[N][nsw].
  * Outputs (any may be NULL): y_out[N][n], t_out[N], sw_out[N][nsw], status[N], stats[N][ORA_NSTATS],
  * dense[N][n_grid][n] (rows for t_grid[k], only filled up to each member's end time),
- * ev_t[N][max_ev], ev_info[N][max_ev] (bit 2i = component i fired, bit 2i+1 = its sign is +1).
+ * ev_t[N][max_ev], ev_info[N][max_ev] (bit 2i = component i fired, bit 2i+1 = its sign is +1, bit 30 = time
+ * event).
  * Returns 0. */
 int ora_simulate(int model, const ora_opts_t *opts, long N, const double *y0, const double *p,
                  const unsigned char *sw0, double t0, double tf, int n_grid, const double *t_grid,

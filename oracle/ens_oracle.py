@@ -14,8 +14,9 @@ LIB = os.path.join(HERE, "libens_oracle.so")
 
 MAX_N = 16
 SOLVERS = {"ExplicitEuler": 0, "RungeKutta4": 1, "RungeKutta34": 2, "Dopri5": 3, "Radau5ODE": 4}
-MODELS = {"vdp": 0, "ball": 1, "robertson": 2, "gyro": 3, "linear": 4, "linear_ev": 5, "extended": 6}
-STATS = ["nsteps", "nfcns", "nerrfails", "njacs", "nlus", "nstatefcns", "nstateevents", "nstepstotal"]
+MODELS = {"vdp": 0, "ball": 1, "robertson": 2, "gyro": 3, "linear": 4, "linear_ev": 5, "extended": 6, "time_ev": 7}
+STATS = ["nsteps", "nfcns", "nerrfails", "njacs", "nlus", "nstatefcns", "nstateevents", "nstepstotal",
+         "ntimeevents"]
 
 
 class Opts(C.Structure):

@@ -69,9 +69,12 @@ def pack(results, max_ev=24):
         for j, (te, info) in enumerate(r["events"][:max_ev]):
             ev_t[i, j] = te
             m = 0
-            for c, v in enumerate(info):
-                if v != 0:
-                    m |= (1 << (2 * c)) | ((1 if v > 0 else 0) << (2 * c + 1))
+            if isinstance(info, str):  # time event
+                m = 1 << 30
+            else:
+                for c, v in enumerate(info):
+                    if v != 0:
+                        m |= (1 << (2 * c)) | ((1 if v > 0 else 0) << (2 * c + 1))
             ev_info[i, j] = m
     out["ev_t"], out["ev_info"], out["nev"] = ev_t, ev_info, nev
     return out
@@ -83,7 +86,35 @@ def save(name, **arrays):
     print("wrote", path, {k: getattr(v, "shape", None) for k, v in arrays.items()})
 
 
+def time_event_cases():
+    """Time events (src/explicit_ode.pyx:212-216,233-264): the reference's test_time_event model with every solver,
+    plus a variant whose last event sits exactly on tfinal and one with an event 2e-16 before it
+    (tests/conftest.py ExplicitTimeEventCloseToFinalTime)."""
+    for solver, opts in (("Dopri5", {}), ("RungeKutta34", {}), ("RungeKutta4", dict(h=0.01)),
+                         ("ExplicitEuler", dict(h=0.01)), ("Radau5ODE", {})):
+        # RungeKutta34 returns ID_PY_OK instead of ID_PY_COMPLETE from the last step of a segment unless state events
+        # or report_continuously are active (runge_kutta.py:657-667), so _simulate never sees its time events (probe:
+        # 0 events, y(5) = 5): its vectors are generated with report_continuously=True, the mode in which the
+        # reference does what it intends.
+        rc = dict(report_continuously=True) if solver == "RungeKutta34" else {}
+        res = [run_member(ref_models.time_ev(), solver, 5.0, **rc, **opts),
+               run_member(ref_models.time_ev((0.5, 1.5, 2.5, 3.0), 0.25, -2.0, 1.0), solver, 3.0, **rc, **opts),
+               run_member(ref_models.time_ev((1.0, 2.0, 2.5, 3.0 - 6e-16), 1.0, 1.0, 0.0), solver, 3.0, **rc, **opts)]
+        for r in res:
+            r["stats"]["ntimeevents"] = len(r["events"])
+        out = pack(res)
+        out["ntimeevents"] = np.array([len(r["events"]) for r in res])
+        out["p"] = np.array([[1.0, 2.0, 2.5, 3.0, 1.0, 1.0], [0.5, 1.5, 2.5, 3.0, 0.25, -2.0],
+                             [1.0, 2.0, 2.5, 3.0 - 6e-16, 1.0, 1.0]])
+        out["y0"] = np.array([[0.0], [1.0], [0.0]])
+        out["tf"] = np.array([5.0, 3.0, 3.0])
+        save("time_ev_" + solver.lower(), **out)
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "time_events":
+        return time_event_cases()
+    time_event_cases()
     # ---- cfg 1: Dopri5 VdP sweep (subset of the N=4096 law) --------------------------------------
     N = 4096
     idx = np.arange(0, N, 64)

@@ -154,3 +154,27 @@ def extended():
     b = Extended(y0=np.array([0.0, -1.0, 0.0]), sw0=[False, True, True], name="extended")
     b.events = []
     return b
+
+
+def time_ev(tes=(1.0, 2.0, 2.5, 3.0), jump=1.0, slope=1.0, y0=0.0):
+    """tests/solvers/test_rungekutta.py:49-82 test_time_event: y' = slope, time events at `tes`, handle_event
+    (event_info = [[], True]): y += jump."""
+    EP = _problem_cls()
+
+    class TimeEv(EP):
+        def rhs(self, t, y):
+            return np.array([slope])
+
+        def time_events(self, t, y, sw):
+            for ev in tes:
+                if t < ev:
+                    return ev
+            return None
+
+        def handle_event(self, solver, event_info):
+            assert event_info[0] == [] and event_info[1]
+            self.events.append((solver.t, "time"))
+            solver.y = solver.y + jump
+    b = TimeEv(y0=np.array([y0], dtype=float), name="time_ev")
+    b.events = []
+    return b

@@ -340,3 +340,29 @@ def test_host_pipeline_with_events_switches_and_failures():
     assert sim.n_not_complete == int(bad.sum()) > 0
     assert ((sim.status == -2) == bad).all() and (sim.t_members[bad] < 2.0).all() and sim.t < 2.0
     assert (sim.t_members[~bad] == 2.0).all()
+
+
+def test_time_events_through_the_solver_class_and_nvrtc():
+    """tests/solvers/test_rungekutta.py:49-82 on the device: built-in model and the same model as NVRTC source."""
+    from assimulo_b200.gpu import Batched_Explicit_Problem, Dopri5, RungeKutta34
+    src = r"""
+__device__ void aens_rhs(double t, const double* y, const unsigned char* sw, const double* p, double* yd) { yd[0] = p[5]; }
+__device__ double aens_time_events(double t, const double* y, const unsigned char* sw, const double* p) {
+    for (int k = 0; k < 4; ++k) if (t < p[k]) return p[k];
+    return AENS_NO_TIME_EVENT;
+}
+__device__ int aens_handle_time_event(double t, double* y, unsigned char* sw, const double* p) { y[0] += p[4]; return 0; }
+"""
+    N = 100
+    p = np.tile(np.array([1.0, 2.0, 2.5, 3.0, 1.0, 1.0]), (N, 1))
+    p[:, 4] = 1.0 + np.arange(N) / N
+    for cls in (Dopri5, RungeKutta34):
+        a = cls(Batched_Explicit_Problem(model="time_ev", y0=np.zeros((N, 1)), p0=p))
+        b = cls(Batched_Explicit_Problem(source=src, n=1, n_p=6, time_events=True, y0=np.zeros((N, 1)), p0=p))
+        for sim in (a, b):
+            sim.simulate(5.0, 100)                                   # exp_sim(5., 100) as in the reference test
+            assert sim.statistics["ntimeevents"] == 4 * N and sim.t == 5.0
+            assert np.allclose(sim.y[:, 0], 5.0 + 4.0 * p[:, 4], rtol=0, atol=1e-9)
+            cnt, te, info = sim.event_log
+            assert (cnt == 4).all() and np.array_equal(te[:, :4], p[:, :4]) and (info[:, :4] == (1 << 30)).all()
+        assert np.array_equal(a.y, b.y)

@@ -46,7 +46,7 @@ def gpu(model, solver, y0, p=None, sw0=None, tf=1.0, arith=None, t_grid=None, ev
            "sums": h.get_stats_sum(), "n": n}
     if t_grid is not None:
         out["dense"] = np.transpose(h.get_dense(), (1, 0, 2))  # -> [N, rows, n] like the oracle
-    if h.n_g:
+    if h.n_g or (h.has_jac & 2):
         out["nev"], out["ev_t"], out["ev_info"] = h.get_events()
     h.close()
     return out
@@ -310,3 +310,32 @@ def test_per_member_failure_status_does_not_abort_the_ensemble():
 def test_tfinal_equal_to_t0_is_a_noop():
     g = gpu("vdp", "Dopri5", [[2.0, -0.6]], [[1.0]], tf=0.0)
     assert g["y"][0].tolist() == [2.0, -0.6] and g["stats"]["nsteps"][0] == 0 and g["status"][0] == 0
+
+
+# ---------------------------------------------------------------------------------------------------------
+# time events: Explicit_Problem.time_events + handle_event(event_info=[[], True])
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("solver,opts", [("Dopri5", {}), ("RungeKutta34", {}), ("RungeKutta4", dict(h=0.01)),
+                                          ("ExplicitEuler", dict(h=0.01)), ("Radau5ODE", {})])
+def test_time_events(solver, opts):
+    gold = golden("time_ev_" + solver.lower())
+    # the reference's vectors, member by member (each has its own tfinal)
+    for k in range(len(gold["tf"])):
+        g = gpu("time_ev", solver, gold["y0"][k:k + 1], gold["p"][k:k + 1], tf=float(gold["tf"][k]), arith="strict", **opts)
+        assert g["status"][0] == 0 and g["t"][0] == gold["t"][k]
+        assert rel_err(g["y"][0], gold["y"][k]) <= 1e-12
+        assert g["stats"]["ntimeevents"][0] == gold["ntimeevents"][k]
+    # an ensemble with different event times per member, both arithmetic modes, against the oracle
+    N = 777
+    rng = np.arange(N) / (N - 1.0)
+    p = np.stack([0.3 + rng, 1.4 + rng, 2.5 + 0.4 * rng, 3.2 + 0.1 * rng, 0.5 + rng, 1.0 - 2.0 * rng], axis=1)
+    y0 = np.zeros((N, 1))
+    o = O.simulate("time_ev", solver, y0, p, tf=4.0, max_ev=24, **opts)
+    for arith in ("strict", "fast"):
+        g = gpu("time_ev", solver, y0, p, tf=4.0, arith=arith, **opts)
+        assert (g["status"] == 0).all() and np.array_equal(g["t"], o["t"])
+        assert rel_err(g["y"], o["y"]) <= (1e-12 if arith == "strict" else 1e-5)
+        assert np.array_equal(g["stats"]["ntimeevents"], o["stats"]["ntimeevents"])
+        assert (g["stats"]["ntimeevents"] == 4).all() and np.array_equal(g["nev"], o["stats"]["ntimeevents"])
+        assert np.array_equal(g["ev_t"][:, :4], o["ev_t"][:, :4])          # time events are hit exactly
+        assert (g["ev_info"][:, :4] == (1 << 30)).all()

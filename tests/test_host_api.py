@@ -114,7 +114,7 @@ def test_shard_bounds_and_assemble():
     y_all = np.stack([y_true[r * B:(r + 1) * B].T for r in range(world)])
     t_all = np.arange(world * B, dtype=float).reshape(world, B)
     st_all = np.zeros((world, B), dtype=np.int32)
-    stats_all = np.ones((world, 8, B), dtype=np.int32)
+    stats_all = np.ones((world, len(parallel.STAT_NAMES), B), dtype=np.int32)
     out = parallel.assemble(t_all, y_all, st_all, stats_all, N)
     assert np.array_equal(out["y"], y_true[:N]) and np.array_equal(out["t"], np.arange(N))
     assert out["statistics"]["nsteps"] == N
