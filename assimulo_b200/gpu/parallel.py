@@ -2,7 +2,7 @@
 
 The members are independent, so the path shards with no data-path collective: rank r of G
 integrates members [r*B, min((r+1)*B, N)) with B = ceil(N/G) on its own GPU, and the final
-``{t, y, status, statistics, event counts/times}`` are exchanged once with ``all_gather`` -- over NCCL / NVLink
+``{t, y, status, statistics, event counts / times / info words}`` are exchanged once with ``all_gather`` -- over NCCL / NVLink
 directly from the library's SoA device buffers when the process group's backend is NCCL, through host tensors
 with gloo (CPU tests).  Dense-output rows stay on the producing GPU.
 
@@ -55,7 +55,8 @@ class _DevView(object):
 
 def gather_final(solver, N_total, group=None):
     """All-gather the final state of a sharded run.  `solver` is this rank's solver after simulate() on its
-    shard.  Returns dict(t[N], y[N,n], status[N], statistics{name:total}, nsteps[N]) on every rank."""
+    shard.  Returns dict(t[N], y[N,n], status[N], statistics{name:total}, stats_per_member{name:[N]}) on every rank,
+    plus event_count[N], event_t[N,slots], event_info[N,slots] (ring order) for models with state or time events."""
     import torch
     import torch.distributed as dist
     world = dist.get_world_size(group)
@@ -63,6 +64,7 @@ def gather_final(solver, N_total, group=None):
     B = solver.N
     backend = dist.get_backend(group)
     h = solver._handle
+    has_events = solver.problem.n_g > 0 or solver.problem.time_events
     if backend == "nccl":
         dev = torch.device("cuda", torch.cuda.current_device())
         solver._handle.sync()
@@ -74,25 +76,43 @@ def gather_final(solver, N_total, group=None):
         y_loc = view(1, (n, B), "<f8")
         st_loc = view(2, (B,), "<i4")
         stats_loc = view(3, (len(STAT_NAMES), B), "<i4")
+        locs = [t_loc, y_loc, st_loc, stats_loc]
+        if has_events:  # event-time ring [slots][B] and its info words, straight from the device log
+            S = int(solver.options["event_slots"])
+            locs += [view(4, (S, B), "<f8"), view(5, (S, B), "<i4")]
         outs = []
-        for loc in (t_loc, y_loc, st_loc, stats_loc):
+        for loc in locs:
             out = torch.empty((world,) + tuple(loc.shape), dtype=loc.dtype, device=dev)
             dist.all_gather_into_tensor(out, loc.contiguous(), group=group)
             outs.append(out)
         torch.cuda.synchronize()
-        t_all, y_all, st_all, stats_all = [o.cpu().numpy() for o in outs]
+        outs = [o.cpu().numpy() for o in outs]
+        t_all, y_all, st_all, stats_all = outs[:4]
+        ev_all = outs[4:]
     else:
         t_loc = torch.from_numpy(np.ascontiguousarray(solver.t_members))
         y_loc = torch.from_numpy(np.ascontiguousarray(solver.y.T))
         st_loc = torch.from_numpy(np.ascontiguousarray(solver.status.astype(np.int32)))
         stats_loc = torch.from_numpy(np.stack([solver.statistics.per_member(k) for k in STAT_NAMES]).astype(np.int32))
+        locs = [t_loc, y_loc, st_loc, stats_loc]
+        if has_events:
+            _, te, info = solver.event_log
+            locs += [torch.from_numpy(np.ascontiguousarray(te.T)), torch.from_numpy(np.ascontiguousarray(info.T.astype(np.int32)))]
         outs = []
-        for loc in (t_loc, y_loc, st_loc, stats_loc):
+        for loc in locs:
             lst = [torch.empty_like(loc) for _ in range(world)]
             dist.all_gather(lst, loc, group=group)
             outs.append(torch.stack(lst).numpy())
-        t_all, y_all, st_all, stats_all = outs
-    return assemble(t_all, y_all, st_all, stats_all, N_total)
+        t_all, y_all, st_all, stats_all = outs[:4]
+        ev_all = outs[4:]
+    res = assemble(t_all, y_all, st_all, stats_all, N_total)
+    if has_events:  # [world, slots, B] -> [N, slots]; ring order as in Batched_Explicit_ODE.event_log
+        S = ev_all[0].shape[1]
+        res["event_t"] = np.transpose(ev_all[0], (0, 2, 1)).reshape(world * B, S)[:N_total]
+        res["event_info"] = np.transpose(ev_all[1], (0, 2, 1)).reshape(world * B, S)[:N_total]
+        spm = res["stats_per_member"]
+        res["event_count"] = spm["nstateevents"] + spm["ntimeevents"]
+    return res
 
 
 def assemble(t_all, y_all, st_all, stats_all, N_total):

@@ -11,6 +11,7 @@ import pytest
 from conftest import ROOT
 
 WORLD = 2
+SLOTS = 16
 N = 37  # deliberately not divisible by WORLD: the last block is padded and trimmed after the gather
 
 
@@ -19,7 +20,13 @@ class _OracleBackedSolver(object):
 
     def __init__(self, problem):
         import ens_oracle as O
-        out = O.simulate("vdp", "Dopri5", problem.y0, problem.p0, tf=2.0, rtol=1e-6, atol=1e-6)
+        if problem.model == "ball":
+            out = O.simulate("ball", "Dopri5", problem.y0, problem.p0, problem.sw0, tf=3.0, max_ev=SLOTS,
+                             rtol=1e-6, atol=1e-6)
+            self.event_log = (out["stats"]["nstateevents"], out["ev_t"], out["ev_info"])
+        else:
+            out = O.simulate("vdp", "Dopri5", problem.y0, problem.p0, tf=2.0, rtol=1e-6, atol=1e-6)
+        self.options = {"event_slots": SLOTS}
         self.problem, self.N = problem, problem.N
         self.t_members, self.y, self.status = out["t"], out["y"], out["status"]
         self._stats = out["stats"]
@@ -47,7 +54,12 @@ def _worker(rank, port, q):
     lo, hi, B = parallel.shard_bounds(N, rank, WORLD)
     assert shard.N == B and np.array_equal(shard.p0[: hi - lo, 0], mu[lo:hi, 0])
     g = parallel.gather_final(_OracleBackedSolver(shard), N)
-    q.put((rank, g["y"], g["t"], g["status"], g["statistics"]["nsteps"], g["stats_per_member"]["nsteps"]))
+    # the same exchange for a model with state events: event counts / times / info words travel too
+    y0b, pb, swb = cases.ball_sweep(N)
+    ball = parallel.shard_problem(Batched_Explicit_Problem(model="ball", y0=y0b, p0=pb, sw0=swb), rank, WORLD)
+    gb = parallel.gather_final(_OracleBackedSolver(ball), N)
+    q.put((rank, g["y"], g["t"], g["status"], g["statistics"]["nsteps"], g["stats_per_member"]["nsteps"],
+           gb["y"], gb["event_count"], gb["event_t"], gb["event_info"]))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -68,7 +80,12 @@ def test_two_rank_gloo_gather_matches_single_process():
         assert p.exitcode == 0
     y0, mu = cases.vdp_sweep(N)
     ref = O.simulate("vdp", "Dopri5", y0, mu, tf=2.0, rtol=1e-6, atol=1e-6)
-    for rank, y, t, st, nsteps, per in res:
+    y0b, pb, swb = cases.ball_sweep(N)
+    refb = O.simulate("ball", "Dopri5", y0b, pb, swb, tf=3.0, max_ev=SLOTS, rtol=1e-6, atol=1e-6)
+    for rank, y, t, st, nsteps, per, yb, evc, evt, evi in res:
+        assert np.array_equal(yb, refb["y"]) and np.array_equal(evc, refb["stats"]["nstateevents"])
+        m = np.isfinite(refb["ev_t"])
+        assert np.array_equal(evt[m], refb["ev_t"][m]) and np.array_equal(evi[m], refb["ev_info"][m])
         assert y.shape == (N, 2)
         assert np.array_equal(y, ref["y"]) and np.array_equal(t, ref["t"])
         assert np.array_equal(per, ref["stats"]["nsteps"]) and nsteps == int(ref["stats"]["nsteps"].sum())
