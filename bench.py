@@ -52,6 +52,27 @@ def ncu_traffic():
     return best
 
 
+def bind_to_gpu_numa_node(gpu_index):
+    """Pin this rank (and the page-locked buffers it is about to allocate) to the CPUs next to its GPU: the e2e leg
+    streams the host arrays over that GPU's PCIe link, and with 8 ranks on a two-socket host unbound processes send
+    half of that traffic across the socket interconnect.  Best effort (NVML); returns the CPU list or None."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        hnd = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(hnd, words)
+        cpus = [64 * w + b for w, m in enumerate(mask) for b in range(64) if (m >> b) & 1]
+        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+        if allowed:
+            bind_to_gpu_numa_node.original = os.sched_getaffinity(0)
+            os.sched_setaffinity(0, allowed)
+            return allowed
+    except Exception:
+        pass
+    return None
+
+
 def vdp_members(n_total, rank, world, per_rank):
     """Members of this rank: 32-member chunks of the global sweep dealt round-robin."""
     chunks = np.arange(rank, n_total // 32, world)[: per_rank // 32]
@@ -283,6 +304,7 @@ def main_gpu(a, rank, world, local_rank):
     json_fd = os.dup(1)
     os.dup2(2, 1)
     torch.cuda.set_device(local_rank)
+    numa = bind_to_gpu_numa_node(local_rank) if world > 1 else None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
@@ -406,6 +428,7 @@ def main_gpu(a, rank, world, local_rank):
                     "path": "Dopri5(Batched_Explicit_Problem).simulate() -> aens_simulate_host through the C ABI: "
                             "pinned host y0/p in, pinned host y out, chunk-pipelined H2D / kernels / D2H"},
             "gpu_launches": int(launches),
+            "cpu_affinity": ("rank 0 bound to %d CPUs next to its GPU (NVML)" % len(numa)) if numa else "unbound",
             "roofline": {"bound": "fp64_fma", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s",
                          "frac": achieved / peak_tflops,
                          "traffic": (ncu_traffic() or (None, None))[0] if a.members == (1 << 23) else None,
@@ -429,6 +452,8 @@ def main_gpu(a, rank, world, local_rank):
             h.close()
             line["configs"] = run_other_configs(local_rank, peak_tflops, hbm)
         if a.cpu_baseline:
+            if getattr(bind_to_gpu_numa_node, "original", None):  # the CPU leg uses every host core again
+                os.sched_setaffinity(0, bind_to_gpu_numa_node.original)
             v, cores, steps, wall, kind = run_cpu_reference(n_total, a.cpu_sample)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": kind,
                                     "sample": "%d members evenly spaced over the sweep, %d accepted steps in %.2f s"
