@@ -333,22 +333,36 @@ AENS_DEV int aens_post_step(S &s, Lane<M> &L, const aens_args_t &a, long long id
 }
 
 /* ------------------------------------------------------------------------------------------------------- */
-/* ExplicitEuler, src/solvers/euler.pyx:570-650                                                              */
+/* ExplicitEuler, src/solvers/euler.pyx:485-692, and ImplicitEuler, src/solvers/euler.pyx:29-483             */
+/* (same integrate() loop, same linear dense output, same post-event partial step; they differ in _step)     */
 /* ------------------------------------------------------------------------------------------------------- */
-template <class M, bool DENSE>
+/* small dense LU of aens_radau5.cuh (Moler's DEC/SOL = LAPACK's partial pivoting) */
+template <int N> AENS_DEV int lu_dec(double *a, int *ip);
+template <int N> AENS_DEV void lu_sol(const double *a, double *b, const int *ip);
+
+template <class M, bool DENSE, bool IMPL = false>
 struct Euler {
     static constexpr bool HAS_DENSE = DENSE;
     static constexpr int N = M::N;
     Lane<M> L;
-    double h, inith;          /* inith = ExplicitEuler._inith: remainder of a grid step cut by an event */
+    double h, inith;          /* inith = _inith: remainder of a grid step cut by an event */
     double yold[DENSE ? N : 1], told, hstep;
     bool pending;
+    /* ImplicitEuler only (euler.pyx:87-92): Jacobian reuse state */
+    double jac[IMPL ? N * N : 1];
+    int since;                /* _steps_since_last_jac */
+    bool needjac, curjac;
 
     AENS_DEV void seg_end() {}
-    AENS_DEV void load_aux(const aens_args_t &a, long long idx) { inith = a.aux[idx]; }
+    AENS_DEV void load_aux(const aens_args_t &a, long long idx) {
+        inith = a.aux[idx];
+        /* a fresh solver object: _needjac = True (euler.pyx:89).  The reference keeps its Jacobian across
+         * simulate() calls of one solver object; the batched solver re-evaluates it at the start of every call. */
+        needjac = true; curjac = false; since = 0;
+    }
     AENS_DEV void store_aux(const aens_args_t &a, long long idx) { a.aux[idx] = inith; }
 
-    AENS_DEV void interp(double x, double *out) { /* euler.pyx:649-650 */
+    AENS_DEV void interp(double x, double *out) { /* euler.pyx:440-441, 649-650 */
         if (DENSE) {
 #pragma unroll
             for (int i = 0; i < N; ++i) out[i] = yold[i] + (x - told) / hstep * (L.y[i] - yold[i]);
@@ -359,7 +373,8 @@ struct Euler {
         seg_init_events(L);
         pending = (inith != 0);
     }
-    AENS_DEV void step(double hs) { /* euler.pyx:636-647 */
+    /* ExplicitEuler._step, euler.pyx:636-647 */
+    AENS_DEV bool step_explicit(double hs) {
         double f[N];
         L.rhs(L.t, L.y, f);
         L.st[AENS_STAT_NFCNS] += 1;
@@ -372,39 +387,135 @@ struct Euler {
             if (DENSE) yold[i] = L.y[i];
             L.y[i] = L.y[i] + hs * f[i];
         }
+        return true;
     }
+    /* ImplicitEuler._jacobian, euler.pyx:322-345 (J column-major) */
+    AENS_DEV void jacobian(const aens_args_t &a, double t, const double *y) {
+        curjac = true; needjac = false; since = 0;
+        if (a.o.usejac && M::HAS_JAC) {
+            M::jac(t, y, L.sw, L.p, jac);
+        } else {
+            double f0[N];
+            L.rhs(t, y, f0);
+#pragma unroll(N <= 4 ? 64 : 1)
+            for (int i = 0; i < N; ++i) {
+                const double delt = sqrt(2.220446049250313e-16 * dmax(dabs(y[i]), 1.e-5));
+                double yp[N], fp[N];
+#pragma unroll(N <= 4 ? 64 : 1)
+                for (int j = 0; j < N; ++j) yp[j] = (j == i) ? y[j] + delt : y[j];
+                L.rhs(t, yp, fp);
+#pragma unroll(N <= 4 ? 64 : 1)
+                for (int j = 0; j < N; ++j) jac[j + i * N] = (fp[j] - f0[j]) / delt;
+            }
+        }
+        L.st[AENS_STAT_NJACS] += 1;
+    }
+    /* ImplicitEuler._step, euler.pyx:363-438: y_{n+1} = y_n + h f(t_{n+1}, y_{n+1}) by a Newton iteration with a lazily
+     * updated Jacobian (refreshed after 20 steps or after a failed iteration) and np.linalg.solve = LU with partial
+     * pivoting.  Returns false when the iteration fails with a current Jacobian ("Newton iteration failed"). */
+    AENS_DEV bool step_implicit(const aens_args_t &a, double hs) {
+        const double t = L.t, tn1 = t + hs;
+        double yn[N], yn1[N], ynew[N], f[N];
+        L.rhs(t, L.y, f);
+        L.st[AENS_STAT_NFCNS] += 1;
+        L.st[AENS_STAT_NSTEPSTOTAL] += 1;
+#pragma unroll(N <= 4 ? 64 : 1)
+        for (int i = 0; i < N; ++i) { yn[i] = L.y[i]; yn1[i] = L.y[i] + hs * f[i]; ynew[i] = yn1[i]; }
+        bool conv = false;
+        for (int j = 0; j < 2 && !conv; ++j) {
+            bool fail = false;
+            if (needjac) jacobian(a, tn1, yn1);
+            double A[N * N];
+            int ip[N];
+#pragma unroll(N <= 4 ? 64 : 1)
+            for (int c = 0; c < N; ++c) {
+#pragma unroll(N <= 4 ? 64 : 1)
+                for (int r = 0; r < N; ++r) A[r + c * N] = hs * jac[r + c * N] - (r == c ? 1.0 : 0.0);
+            }
+            if (lu_dec<N>(A, ip) != 0) { L.status = AENS_ST_RADAU_SINGULAR; return false; } /* LinAlgError */
+            double old_norm = 0.0;
+            int i = 0;
+            for (; i < a.o.newt; ++i) {
+                L.st[AENS_STAT_NNITERS] += 1;
+                double b[N];
+                L.rhs(tn1, yn1, f);
+                L.st[AENS_STAT_NFCNS] += 1;
+#pragma unroll(N <= 4 ? 64 : 1)
+                for (int k = 0; k < N; ++k) b[k] = yn[k] - yn1[k] + hs * f[k];
+                lu_sol<N>(A, b, ip);
+                double sum = 0.0;
+#pragma unroll(N <= 4 ? 64 : 1)
+                for (int k = 0; k < N; ++k) {
+                    ynew[k] = yn1[k] - b[k];
+                    const double w = 1.0 / (a.o.rtol * dabs(yn1[k]) + a.o.atol[k]);
+                    const double prod = (ynew[k] - yn1[k]) * w;
+                    sum += prod * prod;
+                }
+                const double new_norm = sqrt(sum / N); /* WRMS, euler.pyx:349-361 */
+                if (new_norm < 0.1) { conv = true; break; }
+                if (i > 0 && new_norm / old_norm > 2) { fail = true; break; }
+#pragma unroll(N <= 4 ? 64 : 1)
+                for (int k = 0; k < N; ++k) yn1[k] = ynew[k];
+                old_norm = new_norm;
+            }
+            if (!conv && i >= a.o.newt) fail = true;
+            if (fail) {
+                L.st[AENS_STAT_NNFAILS] += 1;
+                if (curjac) { L.status = AENS_ST_NEWTON_FAILED; return false; }
+                needjac = true;
+            }
+            if (conv) {
+                since += 1;
+                L.st[AENS_STAT_NSTEPS] += 1;
+                if (since > 20) needjac = true;
+            }
+        }
+        if (!conv) { L.status = AENS_ST_NEWTON_FAILED; return false; }
+        curjac = false;
+        told = t;
+        hstep = hs;
+#pragma unroll(N <= 4 ? 64 : 1)
+        for (int i = 0; i < N; ++i) {
+            if (DENSE) yold[i] = yn[i];
+            L.y[i] = ynew[i];
+        }
+        return true;
+    }
+    AENS_DEV bool step(const aens_args_t &a, double hs) {
+        if constexpr (IMPL) return step_implicit(a, hs);
+        else return step_explicit(hs);
+    }
+    /* the 1e-15 cut-off exists only in ExplicitEuler (euler.pyx:631-632 vs :218-219) */
+    AENS_DEV double trim(double v) const { return (IMPL || dabs(v) > 1e-15) ? v : 0.0; }
+
     AENS_DEV int attempt(const aens_args_t &a, long long idx) {
-        if (pending) { /* euler.pyx:583-600 */
+        if (pending) { /* euler.pyx:583-600 / 167-184 */
             const double hs = inith;
-            step(hs);
+            if (!step(a, hs)) return AENS_R_ERROR;
             const double tn = told + hs;
             const int flag = aens_post_step<M, Euler>(*this, L, a, idx, tn - hs, tn);
             pending = false;
             if (flag == AENS_R_EVENT) inith = inith - (L.t - told);
             else inith = 0;
             h = dmin(h, dabs(L.tend(a) - L.t));
-            if (flag == AENS_R_EVENT && inith == 0) { /* euler.pyx:629-632 */
-                inith = h - (L.t - told);
-                if (!(dabs(inith) > 1e-15)) inith = 0.0;
-            }
+            if (flag == AENS_R_EVENT && inith == 0) inith = trim(h - (L.t - told)); /* euler.pyx:629-632 / 216-219 */
             return flag;
         }
         const bool inner = (L.t + h < L.tend(a));
         const double hs = h;
-        step(hs);
+        if (!step(a, hs)) return AENS_R_ERROR;
         const double tn = told + hs;
         int flag = aens_post_step<M, Euler>(*this, L, a, idx, tn - hs, tn);
         if (inner) h = dmin(h, dabs(L.tend(a) - L.t));
         if (flag == AENS_R_EVENT) {
-            if (inith == 0) { /* euler.pyx:629-632 */
-                inith = h - (L.t - told);
-                if (!(dabs(inith) > 1e-15)) inith = 0.0;
-            }
+            if (inith == 0) inith = trim(h - (L.t - told)); /* euler.pyx:629-632 / 216-219 */
             return AENS_R_EVENT;
         }
         return inner ? AENS_R_CONTINUE : AENS_R_COMPLETE;
     }
 };
+template <class M, bool DENSE>
+using ImplEuler = Euler<M, DENSE, true>;
 
 /* ------------------------------------------------------------------------------------------------------- */
 /* RungeKutta4, src/solvers/runge_kutta.py:839-862 (no events, no dense output in the reference)            */

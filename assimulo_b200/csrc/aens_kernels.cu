@@ -41,11 +41,13 @@ AENS_DEFINE_KERNEL(KN(aens_rk4_d0_), RK4, KM, false, AENS_MB_RK4)
 AENS_DEFINE_KERNEL(KN(aens_rk34_d1_), RK34, KM, true, AENS_MB_RK34)
 AENS_DEFINE_KERNEL(KN(aens_dopri5_d1_), Dopri5, KM, true, AENS_MB_DOPRI5)
 AENS_DEFINE_KERNEL(KN(aens_radau5_d1_), Radau5, KM, true, AENS_MB_RADAU5)
+AENS_DEFINE_KERNEL(KN(aens_impleuler_d1_), ImplEuler, KM, true, AENS_MB_EULER)
 /* models without events additionally get dense-free variants (no interpolation data kept in registers) */
 AENS_DEFINE_KERNEL(KN(aens_euler_d0_), Euler, KM, kEvents, AENS_MB_EULER)
 AENS_DEFINE_KERNEL(KN(aens_rk34_d0_), RK34, KM, kEvents, AENS_MB_RK34)
 AENS_DEFINE_KERNEL(KN(aens_dopri5_d0_), Dopri5, KM, kEvents, AENS_MB_DOPRI5)
 AENS_DEFINE_KERNEL(KN(aens_radau5_d0_), Radau5, KM, kEvents, AENS_MB_RADAU5)
+AENS_DEFINE_KERNEL(KN(aens_impleuler_d0_), ImplEuler, KM, kEvents, AENS_MB_EULER)
 
 extern "C" const void *AENS_CAT(AENS_CAT(aens_kernels_, AENS_KNAME), AENS_SUF)(int solver, int dense) {
     switch (solver) {
@@ -54,6 +56,8 @@ extern "C" const void *AENS_CAT(AENS_CAT(aens_kernels_, AENS_KNAME), AENS_SUF)(i
     case AENS_SOLVER_RK34: return dense ? (const void *)KN(aens_rk34_d1_) : (const void *)KN(aens_rk34_d0_);
     case AENS_SOLVER_DOPRI5: return dense ? (const void *)KN(aens_dopri5_d1_) : (const void *)KN(aens_dopri5_d0_);
     case AENS_SOLVER_RADAU5: return dense ? (const void *)KN(aens_radau5_d1_) : (const void *)KN(aens_radau5_d0_);
+    case AENS_SOLVER_IMPLEULER:
+        return dense ? (const void *)KN(aens_impleuler_d1_) : (const void *)KN(aens_impleuler_d0_);
     }
     return nullptr;
 }

@@ -77,9 +77,10 @@ cdef extern from "assimulo_cuda.h":
     int aens_set_host_mode(aens_handle_t *h, int mode) nogil
 
 STAT_NAMES = ("nsteps", "nfcns", "nerrfails", "njacs", "nlus", "nstatefcns", "nstateevents", "nstepstotal",
-              "ntimeevents")
+              "ntimeevents", "nniters", "nnfails")
 MODEL_HAS_JAC, MODEL_TIME_EVENTS = 1, 2
-SOLVER_IDS = {"ExplicitEuler": 0, "RungeKutta4": 1, "RungeKutta34": 2, "Dopri5": 3, "Radau5ODE": 4}
+SOLVER_IDS = {"ExplicitEuler": 0, "RungeKutta4": 1, "RungeKutta34": 2, "Dopri5": 3, "Radau5ODE": 4,
+              "ImplicitEuler": 5}
 MAX_N = 16
 
 
@@ -356,7 +357,7 @@ cdef class Handle:
             assert a.dtype == np.intc and a.size == N and a.flags.c_contiguous
             sto = <int*>np.PyArray_DATA(a)
         cdef const double *yptr = &y[0, 0]
-        cdef long long sums[9]
+        cdef long long sums[11]
         cdef long long nbad = 0
         cdef int rc
         with nogil:
@@ -364,16 +365,16 @@ cdef class Handle:
         self._check(rc)
         self.N = N
         self.n_out = 0
-        return {STAT_NAMES[i]: sums[i] for i in range(9)}, nbad
+        return {STAT_NAMES[i]: sums[i] for i in range(11)}, nbad
 
     def get_summary(self):
-        cdef long long s[9]
+        cdef long long s[11]
         cdef long long nbad = 0
         cdef int rc
         with nogil:
             rc = aens_get_summary(self.h, s, &nbad)
         self._check(rc)
-        return {STAT_NAMES[i]: s[i] for i in range(9)}, nbad
+        return {STAT_NAMES[i]: s[i] for i in range(11)}, nbad
 
     def simulate_async(self, double tfinal):
         cdef int rc
@@ -438,12 +439,12 @@ cdef class Handle:
         return out
 
     def get_stats_sum(self):
-        cdef long long s[9]
+        cdef long long s[11]
         cdef int rc
         with nogil:
             rc = aens_get_stats_sum(self.h, s)
         self._check(rc)
-        return {STAT_NAMES[i]: s[i] for i in range(9)}
+        return {STAT_NAMES[i]: s[i] for i in range(11)}
 
     def get_dense(self, slot=None):
         """Row `slot` as [N,n], or all rows as [n_out,N,n] when slot is None."""

@@ -24,7 +24,7 @@ from .problem import Batched_Explicit_Problem
 
 ARITH = {"strict": 0, "fast": 1}
 STAT_NAMES = ("nsteps", "nfcns", "nerrfails", "njacs", "nlus", "nstatefcns", "nstateevents", "nstepstotal",
-              "ntimeevents")
+              "ntimeevents", "nniters", "nnfails")
 
 # status codes (include/assimulo_cuda.h)
 ST_COMPLETE, ST_TERMINATED = 0, 1
@@ -405,6 +405,49 @@ class ExplicitEuler(_FixedStep):
         self.options["h"] = 0.01
         self.options["arith"] = "strict"  # fixed-step parity bar is <=1e-13: reference operation order, no FMA
         self.supports.update(report_continuously=True, interpolated_output=True, state_events=True)
+
+
+class ImplicitEuler(_FixedStep):
+    """Implicit Euler, fixed step, Newton iteration with a lazily updated Jacobian and a per-member dense LU
+    (src/solvers/euler.pyx:29-483).  Per-member failures: status -8 = 'Newton iteration failed'."""
+    _solver_name = "ImplicitEuler"
+
+    def __init__(self, problem, **kw):
+        Batched_Explicit_ODE.__init__(self, problem, **kw)
+        self.options.update(h=0.01, usejac=bool(problem.has_jac), newt=7, atol=1.0e-6 * np.ones(self._leny), rtol=1.0e-6)
+        self.options["arith"] = "strict"  # see ExplicitEuler
+        self.supports.update(report_continuously=True, interpolated_output=True, state_events=True)
+
+    def _set_newt(self, v):
+        try:
+            self.options["newt"] = int(v)
+        except (ValueError, TypeError):
+            raise AssimuloException("The newt must be an integer or float.")
+
+    def _set_usejac(self, v):
+        self.options["usejac"] = bool(v)
+
+    def _set_rtol(self, rtol):
+        try:
+            r = float(rtol)
+        except (ValueError, TypeError):
+            raise AssimuloException("Relative tolerance must be a (scalar) float.")
+        if r <= 0.0:
+            raise AssimuloException("Relative tolerance must be a positive (scalar) float.")
+        self.options["rtol"] = r
+
+    def _set_atol(self, atol):
+        a = np.array(atol, dtype=float) if len(np.array(atol, dtype=float).shape) > 0 else np.array([atol], dtype=float)
+        if len(a) == 1:
+            a = a * np.ones(self._leny)
+        elif len(a) != self._leny:
+            raise AssimuloException("atol must be of length one or same as the dimension of the problem.")
+        self.options["atol"] = a
+
+    newt = _prop("newt", _set_newt, "Maximal number of Newton iterations, default 7.")
+    usejac = _prop("usejac", _set_usejac, "Use the model's analytic Jacobian instead of finite differences.")
+    atol = _prop("atol", _set_atol, "Absolute tolerance(s) of the Newton iteration, default 1e-6.")
+    rtol = _prop("rtol", _set_rtol, "Relative tolerance of the Newton iteration, default 1e-6.")
 
 
 class RungeKutta4(_FixedStep):

@@ -51,12 +51,14 @@ extern "C" {
 #define AENS_ERR_STATE (-4)          /* call order violated (e.g. simulate before set_ensemble) */
 #define AENS_ERR_UNSUPPORTED (-5)    /* model/solver combination not available */
 
-/* solver ids (the five Explicit_ODE subclasses of BASELINE.json) */
+/* solver ids (the five Explicit_ODE subclasses of BASELINE.json + ImplicitEuler) */
 #define AENS_SOLVER_EULER 0          /* src/solvers/euler.pyx:485 ExplicitEuler */
 #define AENS_SOLVER_RK4 1            /* src/solvers/runge_kutta.py:746 RungeKutta4 */
 #define AENS_SOLVER_RK34 2           /* src/solvers/runge_kutta.py:430 RungeKutta34 */
 #define AENS_SOLVER_DOPRI5 3         /* src/solvers/runge_kutta.py:26 Dopri5 */
 #define AENS_SOLVER_RADAU5 4         /* src/solvers/radau5.py:69 Radau5ODE */
+#define AENS_SOLVER_IMPLEULER 5      /* src/solvers/euler.pyx:29 ImplicitEuler */
+#define AENS_NSOLVERS 6
 
 /* per-member status written by aens_simulate (aens_get_final) */
 #define AENS_ST_COMPLETE 0           /* reached tfinal (ID_PY_COMPLETE) */
@@ -65,7 +67,8 @@ extern "C" {
 #define AENS_ST_STEP_TOO_SMALL (-3)  /* DOPRI5 IDID=-3 */
 #define AENS_ST_RADAU_NMAX (-5)      /* RADAU_ERROR_NMAX_TOO_SMALL */
 #define AENS_ST_RADAU_STEP_TOO_SMALL (-6)
-#define AENS_ST_RADAU_SINGULAR (-7)
+#define AENS_ST_RADAU_SINGULAR (-7)   /* also: singular Newton matrix in ImplicitEuler (numpy LinAlgError) */
+#define AENS_ST_NEWTON_FAILED (-8)    /* ImplicitEuler: 'Newton iteration failed' (euler.pyx:415,426) */
 
 /* statistics slots for aens_get_stats (names: src/ode.pyx:153-172) */
 #define AENS_STAT_NSTEPS 0           /* accepted steps */
@@ -77,7 +80,9 @@ extern "C" {
 #define AENS_STAT_NSTATEEVENTS 6
 #define AENS_STAT_NSTEPSTOTAL 7      /* step attempts (DOPRI5 NSTEP, Radau nsteps) */
 #define AENS_STAT_NTIMEEVENTS 8      /* time events (src/explicit_ode.pyx:241-242) */
-#define AENS_NSTATS 9
+#define AENS_STAT_NNITERS 9          /* nonlinear iterations (ImplicitEuler) */
+#define AENS_STAT_NNFAILS 10         /* nonlinear convergence failures (ImplicitEuler) */
+#define AENS_NSTATS 11
 
 /* arithmetic mode */
 #define AENS_ARITH_STRICT 0  /* reference operation order, no FMA contraction, fp64 pow/sqrt/div everywhere */
@@ -87,8 +92,8 @@ typedef struct {
     int solver;          /* AENS_SOLVER_* */
     int arith;           /* AENS_ARITH_* */
     int maxsteps;        /* Dopri5/Radau5ODE: 100000, RungeKutta34: 10000 */
-    int newt;            /* Radau5ODE: max Newton iterations (7) */
-    int usejac;          /* Radau5ODE: 1 = model's analytic Jacobian, 0 = finite differences */
+    int newt;            /* Radau5ODE, ImplicitEuler: max Newton iterations (7) */
+    int usejac;          /* Radau5ODE, ImplicitEuler: 1 = model's analytic Jacobian, 0 = finite differences */
     int reserved;
     double rtol;         /* scalar, broadcast to n (runge_kutta.py:172, radau5.py:374) */
     double atol[AENS_MAX_N];

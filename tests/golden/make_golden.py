@@ -37,7 +37,12 @@ def run_member(problem, solver, tf, ncp=0, report_continuously=False, **opts):
         setattr(sim, k, v)
     if report_continuously:
         sim.report_continuously = True
-    t, y = sim.simulate(tf, ncp)
+    failed = ""
+    try:
+        t, y = sim.simulate(tf, ncp)
+    except Exception as e:  # per-member failure (e.g. ImplicitEuler 'Newton iteration failed'): recorded, not fatal
+        failed = str(e)
+        t, y = list(sim.t_sol), list(sim.y_sol)
     stats = {}
     for k in STAT_KEYS:
         try:
@@ -45,10 +50,18 @@ def run_member(problem, solver, tf, ncp=0, report_continuously=False, **opts):
         except KeyError:
             v = -1
         stats[k] = v
+    if solver in ("RungeKutta4", "ExplicitEuler") and False:
+        pass
     if solver in ("RungeKutta4", "ExplicitEuler"):
         # these keep no counters: accepted steps = len(t_sol)-1 without events
         stats["nsteps"] = len(t) - 1
-    return dict(t_final=float(sim.t), y_final=np.array(sim.y, dtype=float).copy(), stats=stats,
+    extra = {}
+    for k in ("nniters", "nnfails"):
+        try:
+            extra[k] = sim.statistics[k]
+        except KeyError:
+            extra[k] = -1
+    return dict(failed=failed, extra=extra, t_final=float(sim.t), y_final=np.array(sim.y, dtype=float).copy(), stats=stats,
                 t_sol=np.array(t), y_sol=np.array(y), events=list(getattr(problem, "events", [])),
                 sw=list(sim.sw) if sim.sw is not None else [])
 
@@ -111,10 +124,45 @@ def time_event_cases():
         save("time_ev_" + solver.lower(), **out)
 
 
+def implicit_euler_cases():
+    """ImplicitEuler (src/solvers/euler.pyx:29-483): VdP sweep members with analytic and finite-difference
+    Jacobians, the stiff Robertson problem, and the bouncing ball / linear_ev problems with state events."""
+    N = 4096
+    idx = np.arange(0, N, 256)
+    y0, p = cases.vdp_sweep(N, idx)
+    for tag, usejac in (("jac", True), ("fd", False)):
+        res = [run_member(ref_models.vdp(float(mu)), "ImplicitEuler", 2.0, h=1e-3, usejac=usejac) for mu in p[:, 0]]
+        save("impleuler_vdp_" + tag, N=N, idx=idx, mu=p[:, 0], **pack_ie(res))
+    N = 1 << 18
+    idx = np.arange(0, N, N // 8)
+    y0, p = cases.robertson_sweep(N, idx)
+    res = [run_member(ref_models.robertson(*[float(v) for v in pk], with_jac=True), "ImplicitEuler", 4.0, h=1e-2,
+                      rtol=1e-6, atol=cases.ROBERTSON_ATOL) for pk in p]
+    save("impleuler_robertson", N=N, idx=idx, p=p, **pack_ie(res))
+    N = 1 << 20
+    idx = np.arange(0, N, N // 8)
+    y0, p, sw0 = cases.ball_sweep(N, idx)
+    res = [run_member(ref_models.ball(float(h0)), "ImplicitEuler", 3.0, h=1e-3) for h0 in y0[:, 0]]
+    save("impleuler_ball", N=N, idx=idx, h0=y0[:, 0], **pack_ie(res))
+    res = [run_member(ref_models.linear_ev(-1.0, 0.0, 0.5, 1.0), "ImplicitEuler", 2.0)]
+    save("impleuler_linear_ev", **pack_ie(res))
+
+
+def pack_ie(results):
+    out = pack(results)
+    for k in ("nniters", "nnfails"):
+        out[k] = np.array([r["extra"][k] for r in results], dtype=np.int64)
+    out["failed"] = np.array([1 if r["failed"] else 0 for r in results], dtype=np.int64)
+    return out
+
+
 def main():
     if len(sys.argv) > 1 and sys.argv[1] == "time_events":
         return time_event_cases()
+    if len(sys.argv) > 1 and sys.argv[1] == "implicit_euler":
+        return implicit_euler_cases()
     time_event_cases()
+    implicit_euler_cases()
     # ---- cfg 1: Dopri5 VdP sweep (subset of the N=4096 law) --------------------------------------
     N = 4096
     idx = np.arange(0, N, 64)

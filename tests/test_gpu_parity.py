@@ -339,3 +339,76 @@ def test_time_events(solver, opts):
         assert (g["stats"]["ntimeevents"] == 4).all() and np.array_equal(g["nev"], o["stats"]["ntimeevents"])
         assert np.array_equal(g["ev_t"][:, :4], o["ev_t"][:, :4])          # time events are hit exactly
         assert (g["ev_info"][:, :4] == (1 << 30)).all()
+
+
+# ---------------------------------------------------------------------------------------------------------
+# ImplicitEuler
+# ---------------------------------------------------------------------------------------------------------
+IE_KEYS = ("nsteps", "nfcns", "njacs", "nniters", "nnfails")
+
+
+@pytest.mark.parametrize("usejac", [1, 0])
+@pytest.mark.parametrize("arith", ["strict", "fast"])
+def test_implicit_euler_vdp(usejac, arith):
+    N = 2048
+    y0, p = cases.vdp_sweep(N)
+    o = O.simulate("vdp", "ImplicitEuler", y0, p, tf=2.0, h=1e-3, usejac=usejac)
+    g = gpu("vdp", "ImplicitEuler", y0, p, tf=2.0, h=1e-3, usejac=usejac, arith=arith)
+    assert (g["status"] == 0).all() and np.array_equal(g["t"], o["t"])
+    assert rel_err(g["y"], o["y"]) <= (1e-10 if arith == "strict" else 1e-7)
+    if arith == "strict":
+        for k in IE_KEYS:
+            assert np.array_equal(g["stats"][k], o["stats"][k]), k
+    else:
+        assert steps_within(g, o) and abs(int(g["sums"]["nniters"]) - int(o["stats"]["nniters"].sum())) <= 0.02 * o["stats"]["nniters"].sum()
+    # the reference's own vectors
+    gold = golden("impleuler_vdp_" + ("jac" if usejac else "fd"))
+    y0g, pg = cases.vdp_sweep(int(gold["N"]), gold["idx"])
+    gg = gpu("vdp", "ImplicitEuler", y0g, pg, tf=2.0, h=1e-3, usejac=usejac, arith=arith)
+    assert rel_err(gg["y"], gold["y"]) <= (1e-10 if arith == "strict" else 1e-7)
+    if arith == "strict":
+        for k in IE_KEYS:
+            assert np.array_equal(gg["stats"][k], gold[k]), k
+
+
+def test_implicit_euler_events_dense_and_failures():
+    # state events + post-event partial steps (euler.pyx:167-184,216-219)
+    N = 512
+    y0, p, sw0 = cases.ball_sweep(N)
+    o = O.simulate("ball", "ImplicitEuler", y0, p, sw0, tf=3.0, max_ev=24, h=1e-3)
+    g = gpu("ball", "ImplicitEuler", y0, p, sw0, tf=3.0, h=1e-3)
+    assert (g["status"] == 0).all() and rel_err(g["y"], o["y"]) <= 1e-10
+    assert np.array_equal(g["nev"], o["stats"]["nstateevents"]) and np.array_equal(g["sw"], o["sw"])
+    m = np.isfinite(o["ev_t"])
+    assert np.max(np.abs(g["ev_t"][m] - o["ev_t"][m])) < 1e-11
+    for k in IE_KEYS:
+        assert np.array_equal(g["stats"][k], o["stats"][k]), k
+    gold = golden("impleuler_ball")
+    y0g, pg, swg = cases.ball_sweep(int(gold["N"]), gold["idx"])
+    gg = gpu("ball", "ImplicitEuler", y0g, pg, swg, tf=3.0, h=1e-3)
+    assert rel_err(gg["y"], gold["y"]) <= 1e-10 and np.array_equal(gg["nev"], gold["nev"])
+    # linear dense output on a grid
+    grid = np.linspace(0, 2, 41)[1:]
+    y0v, pv = cases.vdp_sweep(300)
+    o = O.simulate("vdp", "ImplicitEuler", y0v, pv, tf=2.0, h=1e-3, usejac=1, t_grid=grid)
+    g = gpu("vdp", "ImplicitEuler", y0v, pv, tf=2.0, h=1e-3, usejac=1, t_grid=grid)
+    assert np.nanmax(np.abs(g["dense"] - o["dense"])) <= 1e-9 and not np.isnan(g["dense"]).any()
+    # 'Newton iteration failed at 0.000000' on Robertson, as in the reference: status -8, state untouched
+    gold = golden("impleuler_robertson")
+    y0r, pr = cases.robertson_sweep(int(gold["N"]), gold["idx"])
+    gr = gpu("robertson", "ImplicitEuler", y0r, pr, tf=4.0, h=1e-2, rtol=1e-6, atol=np.array(cases.ROBERTSON_ATOL), usejac=1)
+    assert (gr["status"] == -8).all() and (gr["t"] == 0.0).all() and np.array_equal(gr["y"], gold["y"])
+    for k in ("njacs", "nniters", "nnfails"):
+        assert np.array_equal(gr["stats"][k], gold[k]), k
+
+
+def test_implicit_euler_solver_class():
+    from assimulo_b200.gpu import Batched_Explicit_Problem, ImplicitEuler
+    y0, mu = cases.vdp_sweep(64)
+    sim = ImplicitEuler(Batched_Explicit_Problem(model="vdp", y0=y0, p0=mu))
+    assert sim.usejac and sim.newt == 7 and sim.h == 0.01
+    sim.h = 1e-3
+    t, y = sim.simulate(2.0, 4)
+    o = O.simulate("vdp", "ImplicitEuler", y0, mu, tf=2.0, h=1e-3, usejac=1)
+    assert len(t) == 5 and rel_err(y[-1], o["y"]) <= 1e-10
+    assert sim.statistics["nniters"] == int(o["stats"]["nniters"].sum()) and sim.statistics["nsteps"] == 64 * 2001
