@@ -1201,7 +1201,17 @@ __device__ __forceinline__ void aens_run(const aens_args_t &a) {
                 }
                 const long long q = a.q_begin + (long long)base + __popc(idle_mask & ((1u << lane) - 1u));
                 if (q < a.q_end) {
-                    idx = a.order ? (long long)a.order[q] : (a.reverse ? a.q_end - 1 - (q - a.q_begin) : q);
+                    if (a.order) {
+                        idx = (long long)a.order[q];
+                    } else if (a.reverse == 2) {
+                        /* two-ended: 32-member batches alternately from the top and from the bottom of the range, so
+                         * that an ensemble sorted by cost is consumed at an even rate from both ends (evens out the
+                         * PCIe demand of the zero-copy host mode); a bijection on the range for any size */
+                        const long long qq = q - a.q_begin, b = qq >> 5, r = qq & 31, k = b >> 1;
+                        idx = (b & 1) ? a.q_begin + (k << 5) + r : a.q_end - 1 - ((k << 5) + r);
+                    } else {
+                        idx = a.reverse ? a.q_end - 1 - (q - a.q_begin) : q;
+                    }
                     s.L.load(a, idx);
                     s.load_aux(a, idx);
                     /* driver loop test, explicit_ode.pyx:209 */

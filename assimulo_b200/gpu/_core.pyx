@@ -309,7 +309,7 @@ cdef class Handle:
         """0 auto, 1 chunked staging pipeline, 2 zero-copy (raises at simulate_host if the arrays are not mappable)."""
         self._check(aens_set_host_mode(self.h, mode))
 
-    def set_fetch_reverse(self, bint reverse):
+    def set_fetch_reverse(self, int reverse):
         self._check(aens_set_fetch_reverse(self.h, reverse))
 
     def simulate_host(self, y0, p, sw0, double t0, double tfinal, out_y=None, out_t=None, out_sw=None,

@@ -177,10 +177,12 @@ class Batched_Explicit_ODE(object):
         self.initialize()
         h = self._get_handle()
         order = self.options["order"]
-        reverse = isinstance(order, str) and order == "descending"
+        reverse = 0
         if isinstance(order, str):
-            if order not in ("ascending", "descending"):
-                raise AssimuloException("order must be None, 'ascending', 'descending' or a permutation of range(N).")
+            if order not in ("ascending", "descending", "two-ended"):
+                raise AssimuloException("order must be None, 'ascending', 'descending', 'two-ended' or a permutation "
+                                        "of range(N).")
+            reverse = {"ascending": 0, "descending": 1, "two-ended": 2}[order]
             order = None
         h.set_fetch_reverse(reverse)
         h.set_opts(self._opts_dict())
@@ -326,7 +328,8 @@ class Batched_Explicit_ODE(object):
 
     def _get_order(self):
         """The order in which members are handed to the warps: None / 'ascending' (by index), 'descending' (from the
-        last member down: for ensembles sorted by increasing cost) or a permutation of range(N)."""
+        last member down: for ensembles sorted by increasing cost), 'two-ended' (32-member batches alternately from
+        both ends: sorted ensembles whose inputs stream from host memory) or a permutation of range(N)."""
         return self.options["order"]
 
     def _set_order(self, v):

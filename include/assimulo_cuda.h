@@ -154,8 +154,10 @@ int aens_set_output(aens_handle_t *h, int n_out, const double *t_out, int event_
  * permutation of 0..N-1 giving the fetch order (e.g. most expensive first). */
 int aens_set_schedule(aens_handle_t *h, int refill_threshold, const int *order);
 
-/* No fetch permutation: hand members out from the highest index downwards (reverse != 0) instead of upwards --
- * for ensembles whose cost grows with the member index (most expensive first, no permutation array to upload). */
+/* No fetch permutation: hand members out from the highest index downwards (reverse = 1) instead of upwards --
+ * for ensembles whose cost grows with the member index (most expensive first, no permutation array to upload) -- or
+ * in 32-member batches alternately from the top and the bottom of the range (reverse = 2): for such ensembles in
+ * zero-copy host mode, where it evens out the rate at which inputs are pulled over PCIe. */
 int aens_set_fetch_reverse(aens_handle_t *h, int reverse);
 
 /* Integrates every member from its current time to tfinal (continuation semantics of ODE.simulate,

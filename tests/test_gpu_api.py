@@ -266,7 +266,7 @@ def test_host_pipeline_equals_the_three_call_path(N, nchunks, mode):
         y0p, mup = _core.pinned_empty((N, 2)), _core.pinned_empty((N, 1))
         y0p[:], mup[:] = y0, mu
         y0, mu = y0p, mup
-    for reverse in (False, True):
+    for reverse in (0, 1, 2):
         h = _core.Handle(0)
         h.set_host_mode(mode)
         h.set_model_builtin("vdp")

@@ -21,7 +21,7 @@ RTOL = 1e-6
 
 
 def gpu(model, solver, y0, p=None, sw0=None, tf=1.0, arith=None, t_grid=None, event_slots=24, order=None,
-        refill=32, **opts):
+        refill=32, reverse=0, **opts):
     from assimulo_b200.gpu import _core
     h = _core.Handle(0)
     h.set_model_builtin(model)
@@ -40,6 +40,7 @@ def gpu(model, solver, y0, p=None, sw0=None, tf=1.0, arith=None, t_grid=None, ev
     h.set_opts(d)
     h.set_output(t_grid, event_slots)
     h.set_schedule(refill, order)
+    h.set_fetch_reverse(reverse)
     h.simulate(tf)
     t, y, sw, st = h.get_final()
     out = {"t": t, "y": y, "sw": sw, "status": st, "stats": {k: h.get_stats(k) for k in _core.STAT_NAMES},
@@ -291,6 +292,9 @@ def test_ragged_sizes_and_schedules():
             g = gpu("vdp", "Dopri5", y0, p, tf=2.0, arith="strict", rtol=1e-6, atol=1e-6, refill=refill,
                     order=rng.permutation(N).astype(np.intc))
             assert np.array_equal(g["y"], base["y"]) and np.array_equal(g["stats"]["nsteps"], base["stats"]["nsteps"])
+            for reverse in (1, 2):      # descending and two-ended fetch: every member exactly once, any size
+                g = gpu("vdp", "Dopri5", y0, p, tf=2.0, arith="strict", rtol=1e-6, atol=1e-6, refill=refill, reverse=reverse)
+                assert np.array_equal(g["y"], base["y"]) and np.array_equal(g["stats"]["nsteps"], base["stats"]["nsteps"])
 
 
 def test_per_member_failure_status_does_not_abort_the_ensemble():

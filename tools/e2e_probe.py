@@ -31,6 +31,11 @@ hsrc = torch.empty(N * 3, dtype=torch.float64).pin_memory()
 print("H2D 201 MB: %.2f ms" % timeit(lambda: d.copy_(hsrc, non_blocking=True)))
 print("D2H 201 MB: %.2f ms" % timeit(lambda: hsrc.copy_(d, non_blocking=True)))
 h.set_host_mode(2)
+for rev in (0, 1, 2):
+    h.set_fetch_reverse(rev)
+    print("zero-copy fetch mode %d: full %.2f ms, kernel %.2f ms" % (
+        rev, timeit(lambda: h.simulate_host(y0, p, None, 0.0, 2.0, out_y=oy)), h.last_kernel_ms()))
+h.set_fetch_reverse(1)
 print("zero-copy: full %.2f ms   no-D2H %.2f ms" % (
     timeit(lambda: h.simulate_host(y0, p, None, 0.0, 2.0, out_y=oy)),
     timeit(lambda: h.simulate_host(y0, p, None, 0.0, 2.0))))
@@ -45,4 +50,6 @@ h.set_ensemble(y0, p, None, 0.0)
 h.set_output(None, 0)
 def k():
     h.reset(); h.simulate(2.0)
-print("reset+kernel resident: %.2f ms (kernel %.2f)" % (timeit(k), h.last_kernel_ms()))
+for rev in (0, 1, 2):
+    h.set_fetch_reverse(rev)
+    print("fetch mode %d reset+kernel resident: %.2f ms (kernel %.2f)" % (rev, timeit(k), h.last_kernel_ms()))
