@@ -75,6 +75,7 @@ cdef extern from "assimulo_cuda.h":
                            long long *n_not_complete) nogil
     int aens_get_summary(aens_handle_t *h, long long *sums, long long *n_not_complete) nogil
     int aens_set_host_mode(aens_handle_t *h, int mode) nogil
+    int aens_reduce_final(aens_handle_t *h, double *mean, double *var, double *mn, double *mx, long long *count) nogil
 
 STAT_NAMES = ("nsteps", "nfcns", "nerrfails", "njacs", "nlus", "nstatefcns", "nstateevents", "nstepstotal",
               "ntimeevents", "nniters", "nnfails")
@@ -366,6 +367,19 @@ cdef class Handle:
         self.N = N
         self.n_out = 0
         return {STAT_NAMES[i]: sums[i] for i in range(11)}, nbad
+
+    def reduce_final(self):
+        """Ensemble statistics of the final states, computed on the device: dict(mean, var, min, max [n], count [n])."""
+        cdef np.ndarray[double, ndim=2, mode="c"] out = np.empty((4, self.n), dtype=np.float64)
+        cdef np.ndarray[np.int64_t, ndim=1, mode="c"] cnt = np.empty(self.n, dtype=np.int64)
+        cdef double *o = &out[0, 0]
+        cdef long long *cp = <long long*>&cnt[0]
+        cdef int n = self.n
+        cdef int rc
+        with nogil:
+            rc = aens_reduce_final(self.h, o, o + n, o + 2 * n, o + 3 * n, cp)
+        self._check(rc)
+        return {"mean": out[0], "var": out[1], "min": out[2], "max": out[3], "count": cnt}
 
     def get_summary(self):
         cdef long long s[11]

@@ -249,6 +249,13 @@ class Batched_Explicit_ODE(object):
             return self.t_sol, self.y_sol  # list of [N, n] rows, no ensemble-sized stacking copy
         return self.t_sol, np.array(self.y_sol)
 
+    def ensemble_statistics(self):
+        """mean / var / min / max of the current (final) states over the members that completed, reduced on the device
+        (ensemble outputs without materialising ensemble-sized arrays on the host)."""
+        if self._handle is None or not self._launched:
+            raise AssimuloException("simulate() first.")
+        return self._handle.reduce_final()
+
     @property
     def status(self):
         """Per-member status codes (include/assimulo_cuda.h AENS_ST_*); 0 = reached tfinal."""

@@ -191,6 +191,10 @@ int aens_get_summary(aens_handle_t *h, long long *sums /*[AENS_NSTATS]*/, long l
 int aens_get_final(aens_handle_t *h, double *t, double *y, unsigned char *sw, int *status);
 int aens_get_stats(aens_handle_t *h, int which, int *out /*[N]*/);
 int aens_get_stats_sum(aens_handle_t *h, long long *sums /*[AENS_NSTATS]*/);
+/* Ensemble statistics of the final states computed on the device (nothing ensemble-sized crosses PCIe): per state
+ * component, over the members whose status is AENS_ST_COMPLETE: mean[n], var[n] (population variance), min[n],
+ * max[n], count[n].  Any pointer may be NULL. */
+int aens_reduce_final(aens_handle_t *h, double *mean, double *var, double *min, double *max, long long *count);
 /* dense output row `slot` (0..n_out-1) as y_out[N][n]; rows beyond a member's end time are NaN */
 int aens_get_dense(aens_handle_t *h, int slot, double *y_out);
 /* whole buffer, y_out[n_out][N][n] */

@@ -366,3 +366,28 @@ __device__ int aens_handle_time_event(double t, double* y, unsigned char* sw, co
             cnt, te, info = sim.event_log
             assert (cnt == 4).all() and np.array_equal(te[:, :4], p[:, :4]) and (info[:, :4] == (1 << 30)).all()
         assert np.array_equal(a.y, b.y)
+
+
+def test_ensemble_statistics_on_device():
+    """aens_reduce_final: mean / var / min / max of the final states over the completed members, on the device."""
+    from assimulo_b200.gpu import Batched_Explicit_Problem, Dopri5
+    N = 5000
+    y0, mu = cases.vdp_sweep(N)
+    sim = Dopri5(Batched_Explicit_Problem(model="vdp", y0=y0, p0=mu))
+    sim.simulate(2.0)
+    st = sim.ensemble_statistics()
+    y = sim.y
+    assert (st["count"] == N).all()
+    np.testing.assert_allclose(st["mean"], y.mean(axis=0), rtol=1e-12, atol=1e-13)
+    np.testing.assert_allclose(st["var"], y.var(axis=0), rtol=1e-10)
+    assert np.array_equal(st["min"], y.min(axis=0)) and np.array_equal(st["max"], y.max(axis=0))
+    # failed members are left out
+    sim = Dopri5(Batched_Explicit_Problem(model="vdp", y0=y0, p0=mu))
+    sim.maxsteps = 60
+    sim.simulate(2.0)
+    ok = sim.status == 0
+    assert 0 < ok.sum() < N
+    st = sim.ensemble_statistics()
+    assert (st["count"] == ok.sum()).all()
+    np.testing.assert_allclose(st["mean"], sim.y[ok].mean(axis=0), rtol=1e-12, atol=1e-13)
+    assert np.array_equal(st["min"], sim.y[ok].min(axis=0)) and np.array_equal(st["max"], sim.y[ok].max(axis=0))
