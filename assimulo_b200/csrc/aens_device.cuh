@@ -56,23 +56,17 @@ AENS_DEV double dmin(double a, double b) { return a <= b ? a : b; }
 AENS_DEV float flg2(float x) { float r; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 AENS_DEV float fex2(float x) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 AENS_DEV float fpow(float x, float e) { return fex2(e * flg2(x)); }
-/* reciprocal of a strictly positive, normal fp64 number for the error norms: MUFU.RCP64H seed (~2^-23) + one
- * Newton step -> ~2^-46 relative, far below what an accept/reject decision can see */
 /* the argument of larger magnitude, decided on the high words (sign, exponent, 20 mantissa bits): when they tie the
  * two magnitudes agree to 2^-20, which is all a tolerance scale needs; keeps the compare off the fp64 pipe */
 AENS_DEV double absmax_hi(double a, double b) {
     return ((__double2hiint(a) & 0x7fffffff) >= (__double2hiint(b) & 0x7fffffff)) ? a : b;
 }
+/* MUFU.RCP64H seed of 1/b (~2^-23 relative) for the error norms: a perturbation of the tolerance scale, far below
+ * what an accept/reject decision can see; r_recip() adds one Newton step (2^-46) where a quotient feeds a state */
 AENS_DEV double rcp_seed(double b) {
     double r;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b));
     return r;
-}
-AENS_DEV double rcp_pos(double b) {
-    double r;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b));
-    const double e = fma(-b, r, 1.0);
-    return fma(r, e, r);
 }
 #endif
 
@@ -526,11 +520,16 @@ struct RK4 {
     static constexpr int N = M::N;
     Lane<M> L;
     double h;
+    double h6;                /* h / 6. of the current h: the fp64 division runs only when h changes (last step), and
+                               * yields the same double as recomputing it every step like the reference does */
     AENS_DEV void seg_end() {}
     AENS_DEV void load_aux(const aens_args_t &, long long) {}
     AENS_DEV void store_aux(const aens_args_t &, long long) {}
     AENS_DEV void interp(double, double *) {}
-    AENS_DEV void seg_init(const aens_args_t &a, long long) { h = dmin(a.o.h, dabs(L.tend(a) - L.t)); }
+    AENS_DEV void seg_init(const aens_args_t &a, long long) {
+        h = dmin(a.o.h, dabs(L.tend(a) - L.t));
+        h6 = h / 6.;
+    }
     AENS_DEV int attempt(const aens_args_t &a, long long) {
         const bool inner = (L.t + h < L.tend(a));
         double Y1[N], Y2[N], Y3[N], Y4[N], arg[N];
@@ -545,14 +544,17 @@ struct RK4 {
 #pragma unroll
         for (int i = 0; i < N; ++i) arg[i] = L.y[i] + h * Y3[i];
         L.rhs(t + h, arg, Y4);
-        const double h6 = h / 6.;
 #pragma unroll
         for (int i = 0; i < N; ++i) L.y[i] = L.y[i] + h6 * (Y1[i] + 2. * Y2[i] + 2. * Y3[i] + Y4[i]);
         L.t = t + h;
         L.st[AENS_STAT_NFCNS] += 4;
         L.st[AENS_STAT_NSTEPS] += 1;
         L.st[AENS_STAT_NSTEPSTOTAL] += 1;
-        if (inner) { h = dmin(h, dabs(L.tend(a) - L.t)); return AENS_R_CONTINUE; }
+        if (inner) {
+            const double hn = dmin(h, dabs(L.tend(a) - L.t));
+            if (hn != h) { h = hn; h6 = hn / 6.; }
+            return AENS_R_CONTINUE;
+        }
         return AENS_R_COMPLETE;
     }
 };
@@ -612,7 +614,11 @@ struct RK34 {
 #pragma unroll
         for (int i = 0; i < N; ++i) arg[i] = L.y[i] + h * Y3[i];
         L.rhs(t + h, arg, Y4);
+#if AENS_STRICT
         const double h6 = h / 6.0;
+#else
+        const double h6 = h * (1.0 / 6.0);
+#endif
         double err2 = 0.;
 #pragma unroll
         for (int i = 0; i < N; ++i) {
@@ -620,7 +626,7 @@ struct RK34 {
             const double e = h6 * (2.0 * Y2[i] + Z3[i] - 2.0 * Y3[i] - Y4[i]) / sc[i];
             err2 = fma(e, e, err2); /* numpy x.dot(x) = OpenBLAS ddot accumulates fused (oracle/ens_oracle.c) */
 #else
-            const double e = h6 * (2.0 * Y2[i] + Z3[i] - 2.0 * Y3[i] - Y4[i]) * rcp_pos(sc[i]);
+            const double e = h6 * (2.0 * Y2[i] + Z3[i] - 2.0 * Y3[i] - Y4[i]) * rcp_seed(sc[i]); /* 2^-23 on the tolerance */
             err2 = fma(e, e, err2);
 #endif
         }

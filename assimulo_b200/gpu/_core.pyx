@@ -41,6 +41,7 @@ cdef extern from "assimulo_cuda.h":
     int aens_destroy(aens_handle_t **h) nogil
     const char *aens_last_error(const aens_handle_t *h) nogil
     const char *aens_version() nogil
+    int aens_nstats() nogil
     int aens_set_model_builtin(aens_handle_t *h, const char *name) nogil
     int aens_set_model_source(aens_handle_t *h, const char *src, int n, int n_p, int n_g, int n_sw, int has_jac) nogil
     int aens_model_dims(const aens_handle_t *h, int *n, int *n_p, int *n_g, int *n_sw, int *has_jac) nogil
@@ -94,6 +95,12 @@ class AensError(RuntimeError):
 
 def version():
     return aens_version().decode()
+
+
+if aens_nstats() != len(STAT_NAMES) or aens_nstats() != 11:
+    # the fixed-size statistic buffers below (long long[11]) must match the library this module was linked against
+    raise ImportError("libassimulo_cuda.so reports %d statistic slots, this binding was built for %d"
+                      % (aens_nstats(), len(STAT_NAMES)))
 
 
 def default_opts(solver):

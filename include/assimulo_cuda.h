@@ -114,6 +114,9 @@ int aens_create(int device, aens_handle_t **h);
 int aens_destroy(aens_handle_t **h);
 const char *aens_last_error(const aens_handle_t *h);
 const char *aens_version(void);
+/* AENS_NSTATS of the library that is actually loaded: the length every `sums` / statistics array must have (for
+ * callers that cannot include this header, e.g. ctypes) */
+int aens_nstats(void);
 
 /* Models.  Built-ins: "vdp" "ball" "robertson" "gyro" "linear" "linear_ev" "extended" "time_ev".
  * aens_set_model_source compiles `cuda_src` with NVRTC for sm_100a.  The source must define

@@ -209,7 +209,8 @@ def test_raw_c_abi_through_ctypes():
     assert lib.aens_get_stats(h, 0, ns.ctypes.data_as(C.c_void_p)) == 0
     ref = O.simulate("vdp", "Dopri5", y0, mu, tf=2.0)
     assert np.array_equal(ns, ref["stats"]["nsteps"]) and rel_err(y, ref["y"]) < 1e-10 and (st == 0).all()
-    sums = (C.c_longlong * 8)()
+    lib.aens_nstats.restype = C.c_int
+    sums = (C.c_longlong * lib.aens_nstats())()   # sized by the library, not by a literal
     assert lib.aens_get_stats_sum(h, sums) == 0 and sums[0] == ns.sum()
     assert lib.aens_reset(h) == 0 and lib.aens_simulate(h, 2.0) == 0
     y2 = np.empty((N, 2))
