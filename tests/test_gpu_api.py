@@ -392,3 +392,37 @@ def test_ensemble_statistics_on_device():
     assert (st["count"] == ok.sum()).all()
     np.testing.assert_allclose(st["mean"], sim.y[ok].mean(axis=0), rtol=1e-12, atol=1e-13)
     assert np.array_equal(st["min"], sim.y[ok].min(axis=0)) and np.array_equal(st["max"], sim.y[ok].max(axis=0))
+
+
+def test_maximum_state_dimension_nvrtc_model_against_analytic_solution():
+    """n = AENS_MAX_N = 16 through NVRTC: exercises the wide-system code paths (row-sum Dopri5 stages, rolled LU of
+    Radau5ODE / ImplicitEuler in local memory, FD and analytic Jacobians).  y_i' = -lam_i y_i + c, lam_i = p0 (i+1)."""
+    from assimulo_b200.gpu import Batched_Explicit_Problem, Dopri5, RungeKutta34, RungeKutta4, Radau5ODE, ImplicitEuler
+    n = 16
+    src = r"""
+__device__ void aens_rhs(double t, const double* y, const unsigned char* sw, const double* p, double* yd) {
+    for (int i = 0; i < 16; ++i) yd[i] = -p[0] * (i + 1) * y[i] + p[1];
+}
+__device__ void aens_jac(double t, const double* y, const unsigned char* sw, const double* p, double* J) {
+    for (int k = 0; k < 256; ++k) J[k] = 0.0;
+    for (int i = 0; i < 16; ++i) J[i + 16 * i] = -p[0] * (i + 1);
+}
+"""
+    N = 300
+    p = np.stack([0.5 + np.arange(N) / N, 0.1 + 0.0 * np.arange(N)], axis=1)
+    y0 = np.tile(1.0 + 0.1 * np.arange(n), (N, 1))
+    lam = p[:, :1] * (np.arange(n)[None, :] + 1.0)
+    tf = 1.5
+    exact = (y0 - p[:, 1:2] / lam) * np.exp(-lam * tf) + p[:, 1:2] / lam
+    prob = lambda: Batched_Explicit_Problem(source=src, n=n, n_p=2, has_jac=True, y0=y0, p0=p)  # noqa: E731
+    for cls, tol, opts in ((Dopri5, 2e-5, {}), (RungeKutta34, 2e-5, {}), (RungeKutta4, 1e-6, dict(h=0.005)),
+                           (Radau5ODE, 2e-5, dict(usejac=True)), (Radau5ODE, 2e-5, dict(usejac=False)),
+                           (ImplicitEuler, 2e-2, dict(h=0.005, usejac=True)),
+                           (ImplicitEuler, 2e-2, dict(h=0.005, usejac=False))):
+        sim = cls(prob())
+        for k, v in opts.items():
+            setattr(sim, k, v)
+        sim.simulate(tf)
+        assert sim.n_not_complete == 0, cls.__name__
+        err = np.max(np.abs(sim.y - exact) / np.maximum(np.abs(exact), 1e-3))
+        assert err < tol, (cls.__name__, opts, err)
