@@ -426,3 +426,66 @@ __device__ void aens_jac(double t, const double* y, const unsigned char* sw, con
         assert sim.n_not_complete == 0, cls.__name__
         err = np.max(np.abs(sim.y - exact) / np.maximum(np.abs(exact), 1e-3))
         assert err < tol, (cls.__name__, opts, err)
+
+
+def test_full_size_properties_cfg3_ball_events():
+    """BASELINE cfg 3 at full size (2^20 bouncing balls): every member's event log obeys the physics (impact times
+    increase, indicators alternate impact / apex), counts are monotone in the drop height, and a strided sample
+    matches the oracle event for event."""
+    from assimulo_b200.gpu import Batched_Explicit_Problem, Dopri5
+    N = 1 << 20
+    y0, p, sw0 = cases.ball_sweep(N)
+    sim = Dopri5(Batched_Explicit_Problem(model="ball", y0=y0, p0=p, sw0=sw0))
+    sim.options["event_slots"] = 16
+    sim.simulate(3.0)
+    assert sim.n_not_complete == 0 and sim.t == 3.0
+    cnt, te, info = sim.event_log
+    assert sim.statistics["nstateevents"] == int(cnt.astype(np.int64).sum()) and cnt.min() >= 3 and cnt.max() <= 16
+    first = te[:, 0]
+    assert np.allclose(first, np.sqrt(2.0 * y0[:, 0] / 9.81), rtol=0, atol=1e-7)      # first impact: analytic
+    k = np.arange(16)[None, :] < cnt[:, None]
+    dte = np.diff(te, axis=1)
+    assert (dte[k[:, 1:]] > 0).all()                                                   # chronological
+    assert (info[:, 0::2][k[:, 0::2]] == 0b01).all() and (info[:, 1::2][k[:, 1::2]] == 0b0100).all()  # impact (g0: + to -), apex (g1: + to -), ...
+    assert (np.diff(cnt.astype(int)) <= 0).all()                                       # higher drop -> fewer bounces by t=3
+    assert (sim.y[:, 0] > -1e-9).all()                                                 # nobody fell through the floor
+    idx = np.arange(0, N, 8192)
+    o = O.simulate("ball", "Dopri5", y0[idx], p[idx], sw0[idx], tf=3.0, max_ev=16, rtol=1e-6, atol=1e-6)
+    assert np.array_equal(cnt[idx], o["stats"]["nstateevents"]) and rel_err(sim.y[idx], o["y"]) <= 1e-5
+    m = np.isfinite(o["ev_t"])
+    assert np.max(np.abs(te[idx][m] - o["ev_t"][m])) < 1e-9
+
+
+def test_full_size_properties_cfg4_robertson_and_cfg5_gyro():
+    """cfg 4 (2^18 Robertson, Radau5ODE): mass conservation y1+y2+y3 = 1 and positivity for every member, strided
+    oracle sample.  cfg 5 (gyro, Dopri5 rtol 1e-8, dense rows; 2^18 of the 2^22 members to keep the test's host arrays
+    small -- bench.py runs the full size): |pi| is conserved and Q stays orthogonal in every dense row."""
+    from assimulo_b200.gpu import Batched_Explicit_Problem, Dopri5, Radau5ODE
+    N = 1 << 18
+    y0, p = cases.robertson_sweep(N)
+    sim = Radau5ODE(Batched_Explicit_Problem(model="robertson", y0=y0, p0=p))
+    sim.rtol, sim.atol, sim.usejac = 1e-6, cases.ROBERTSON_ATOL, True
+    sim.simulate(40.0)
+    assert sim.n_not_complete == 0
+    assert np.max(np.abs(sim.y.sum(axis=1) - 1.0)) < 1e-9 and (sim.y > -1e-9).all()
+    idx = np.arange(0, N, 1024)
+    o = O.simulate("robertson", "Radau5ODE", y0[idx], p[idx], tf=40.0, rtol=1e-6, atol=cases.ROBERTSON_ATOL, usejac=1)
+    assert rel_err(sim.y[idx], o["y"]) <= 1e-5
+    ns = sim.statistics.per_member("nsteps")
+    assert abs(int(ns[idx].sum()) - int(o["stats"]["nsteps"].sum())) <= 0.02 * o["stats"]["nsteps"].sum()
+    # gyro
+    Ng = 1 << 22
+    idx = np.arange(0, Ng, 16)
+    y0, p = cases.gyro_sweep(Ng, idx)
+    sim = Dopri5(Batched_Explicit_Problem(model="gyro", y0=y0, p0=p))
+    sim.rtol, sim.atol = 1e-8, 1e-8
+    t, y = sim.simulate(0.1, 10)
+    assert sim.n_not_complete == 0 and y.shape == (11, len(idx), 12) and np.isfinite(y).all()
+    pi2 = (y[:, :, :3] ** 2).sum(axis=2)
+    assert np.max(np.abs(pi2 / pi2[0] - 1.0)) < 1e-5                                   # |pi| conserved
+    Q = y[:, :, 3:].reshape(11, len(idx), 3, 3)
+    QtQ = np.einsum("tmij,tmik->tmjk", Q, Q)
+    assert np.max(np.abs(QtQ - np.eye(3))) < 1e-5                                      # Q orthogonal
+    sub = np.arange(0, len(idx), 4096)
+    o = O.simulate("gyro", "Dopri5", y0[sub], p[sub], tf=0.1, rtol=1e-8, atol=1e-8, t_grid=np.linspace(0, 0.1, 11)[1:])
+    assert np.max(np.abs(np.transpose(y[1:, sub], (1, 0, 2)) - o["dense"]) / np.maximum(np.abs(o["dense"]), 1.0)) <= 1e-7
