@@ -60,8 +60,11 @@ class Batched_Explicit_ODE(object):
         if not isinstance(problem, Batched_Explicit_Problem):
             raise Explicit_ODE_Exception("The problem needs to be a subclass of a Batched_Explicit_Problem.")
         self.problem = problem
-        self.options = {"arith": "fast", "refill_threshold": 32, "order": None, "event_slots": 16,
-                        "verbosity": 30, "store_event_points": True, "reuse_buffers": False, "host_chunks": None}
+        # the reference's general options (src/ode.pyx:45-52) followed by the batched solver's own
+        self.options = {"report_continuously": False, "display_progress": True, "verbosity": 30, "backward": False,
+                        "store_event_points": True, "time_limit": 0, "clock_step": False, "num_threads": 1,
+                        "arith": "fast", "refill_threshold": 32, "order": None, "event_slots": 16,
+                        "reuse_buffers": False, "host_chunks": None}
         self.supports = {"state_events": False, "interpolated_output": False, "report_continuously": False}
         self.problem_info = {"dim": problem.n, "dimRoot": problem.n_g, "state_events": problem.n_g > 0,
                              "jac_fcn": problem.has_jac, "switches": problem.n_sw > 0}
@@ -309,6 +312,53 @@ class Batched_Explicit_ODE(object):
             print(" %-22s : %d" % (k, self.statistics[k]))
         print("\nSolver options:\n\n Solver                  : %s (batched, %s arithmetic)" %
               (self._solver_name, self.options["arith"]))
+
+    # ---- the reference's general solver options (src/ode.pyx:343-507): same names, same validation ------
+    def _set_verbosity(self, verb):
+        try:
+            self.options["verbosity"] = int(verb)
+        except Exception:
+            raise AssimuloException("Verbosity must be an integer.")
+    verbosity = property(lambda self: self.options["verbosity"], _set_verbosity,
+                         doc="QUIET 50 / WHISPER 40 / NORMAL 30 / LOUD 20 / SCREAM 10 (src/ode.pyx:343-370).")
+
+    def _set_time_limit(self, time_limit):
+        if time_limit < 0:
+            raise AssimuloException("The time limit must be positive or zero.")
+        self.options["time_limit"] = time_limit
+    time_limit = property(lambda self: self.options["time_limit"], _set_time_limit,
+                          doc="Accepted for compatibility; one launch integrates the whole ensemble, there is no "
+                              "per-step host loop to interrupt (src/ode.pyx:372-392).")
+
+    def _set_display_progress(self, v):
+        self.options["display_progress"] = bool(v)
+    display_progress = property(lambda self: self.options["display_progress"], _set_display_progress)
+
+    def _set_report_continuously(self, v):
+        self.options["report_continuously"] = bool(v)
+    report_continuously = property(lambda self: self.options["report_continuously"], _set_report_continuously,
+                                   doc="Accepted for compatibility: with an output grid the device always reports "
+                                       "interpolated rows step by step (the reference's report_continuously=True "
+                                       "semantics, SURVEY A.7); without one only initial and final rows exist.")
+
+    def _set_number_threads(self, v):
+        self.options["num_threads"] = int(v)
+    num_threads = property(lambda self: self.options["num_threads"], _set_number_threads)
+
+    def _set_store_event_points(self, v):
+        self.options["store_event_points"] = bool(v)
+    store_event_points = property(lambda self: self.options["store_event_points"], _set_store_event_points,
+                                  doc="Event points are always available through event_log (src/ode.pyx:456-475).")
+
+    def _set_clock_step(self, v):
+        self.options["clock_step"] = v
+    clock_step = property(lambda self: self.options["clock_step"], _set_clock_step)
+
+    def _set_backward(self, v):
+        if bool(v):
+            raise AssimuloException("Backward integration is not available in the batched solvers.")
+        self.options["backward"] = False
+    backward = property(lambda self: self.options["backward"], _set_backward)
 
     # ---- options shared by all batched solvers ------------------------------------------------------
     def _get_arith(self):

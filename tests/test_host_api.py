@@ -124,3 +124,24 @@ def test_shard_bounds_and_assemble():
     assert parts[3].p0[:, 0].tolist() == [9.0, 9.0, 9.0]          # padded with copies of the last member
     order = parallel.cost_balanced_order([1.0, 5.0, 3.0])
     assert order.tolist() == [1, 2, 0]
+
+
+def test_general_solver_options_of_the_reference():
+    """src/ode.pyx:343-507: verbosity / time_limit / display_progress / report_continuously / num_threads /
+    store_event_points / clock_step / backward exist with the reference's validation."""
+    from assimulo_b200.gpu import Batched_Explicit_Problem, Dopri5, AssimuloException
+    sim = Dopri5(Batched_Explicit_Problem(model="vdp", y0=[2.0, -0.6], p0=[[1.0], [2.0]]))
+    assert sim.verbosity == 30 and sim.report_continuously is False and sim.store_event_points is True
+    sim.verbosity = 50
+    sim.report_continuously = 1
+    sim.display_progress = False
+    sim.num_threads = 4
+    sim.time_limit = 10
+    assert sim.options["verbosity"] == 50 and sim.report_continuously is True and sim.num_threads == 4
+    with pytest.raises(AssimuloException):
+        sim.verbosity = "loud"
+    with pytest.raises(AssimuloException):
+        sim.time_limit = -1
+    with pytest.raises(AssimuloException):
+        sim.backward = True
+    assert sim.backward is False
