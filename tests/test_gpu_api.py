@@ -489,3 +489,26 @@ def test_full_size_properties_cfg4_robertson_and_cfg5_gyro():
     sub = np.arange(0, len(idx), 4096)
     o = O.simulate("gyro", "Dopri5", y0[sub], p[sub], tf=0.1, rtol=1e-8, atol=1e-8, t_grid=np.linspace(0, 0.1, 11)[1:])
     assert np.max(np.abs(np.transpose(y[1:, sub], (1, 0, 2)) - o["dense"]) / np.maximum(np.abs(o["dense"]), 1.0)) <= 1e-7
+
+
+@pytest.mark.parametrize("name,opts", [("Dopri5", dict(rtol=1e-6, atol=1e-6)), ("RungeKutta34", dict(rtol=1e-6, atol=1e-6)),
+                                        ("Radau5ODE", dict(rtol=1e-6, atol=1e-6, usejac=True)),
+                                        ("ImplicitEuler", dict(h=1e-3, usejac=True))])
+def test_continuation_restarts_like_the_reference(name, opts):
+    """A second simulate() continues from the device state: the reference re-initialises the solver (HINIT, FACOLD,
+    Radau reinit, first-step logic) at the restart point (src/ode.pyx:195-196, explicit_ode.pyx:190-204), so 0 -> 1 -> 2
+    must equal the oracle started at t = 1 from the state it reached at t = 1 -- states, times and statistics."""
+    import assimulo_b200.gpu as G
+    N = 500
+    y0, mu = cases.vdp_sweep(N)
+    sim = getattr(G, name)(G.Batched_Explicit_Problem(model="vdp", y0=y0, p0=mu))
+    sim.arith = "strict"
+    for k, v in opts.items():
+        setattr(sim, k, v)
+    sim.simulate(1.0)
+    o1 = O.simulate("vdp", name, y0, mu, tf=1.0, **{k: (int(v) if k == "usejac" else v) for k, v in opts.items()})
+    assert rel_err(sim.y, o1["y"]) <= 1e-10 and sim.statistics["nsteps"] == int(o1["stats"]["nsteps"].sum())
+    sim.simulate(2.0)
+    o2 = O.simulate("vdp", name, o1["y"], mu, t0=1.0, tf=2.0, **{k: (int(v) if k == "usejac" else v) for k, v in opts.items()})
+    assert sim.t == 2.0 and rel_err(sim.y, o2["y"]) <= 1e-9
+    assert sim.statistics["nsteps"] == int(o2["stats"]["nsteps"].sum())        # statistics restart with every simulate()
