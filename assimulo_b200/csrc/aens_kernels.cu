@@ -42,6 +42,7 @@ AENS_DEFINE_KERNEL(KN(aens_rk34_d1_), RK34, KM, true, AENS_MB_RK34)
 AENS_DEFINE_KERNEL(KN(aens_dopri5_d1_), Dopri5, KM, true, AENS_MB_DOPRI5)
 AENS_DEFINE_KERNEL(KN(aens_radau5_d1_), Radau5, KM, true, AENS_MB_RADAU5)
 AENS_DEFINE_KERNEL(KN(aens_impleuler_d1_), ImplEuler, KM, true, AENS_MB_EULER)
+AENS_DEFINE_KERNEL(KN(aens_rodas_d1_), Rodas, KM, true, AENS_MB_RADAU5)
 /* models without events additionally get dense-free variants (no interpolation data kept in registers) */
 AENS_DEFINE_KERNEL(KN(aens_euler_d0_), Euler, KM, kEvents, AENS_MB_EULER)
 AENS_DEFINE_KERNEL(KN(aens_rk34_d0_), RK34, KM, kEvents, AENS_MB_RK34)
@@ -58,6 +59,7 @@ extern "C" const void *AENS_CAT(AENS_CAT(aens_kernels_, AENS_KNAME), AENS_SUF)(i
     case AENS_SOLVER_RADAU5: return dense ? (const void *)KN(aens_radau5_d1_) : (const void *)KN(aens_radau5_d0_);
     case AENS_SOLVER_IMPLEULER:
         return dense ? (const void *)KN(aens_impleuler_d1_) : (const void *)KN(aens_impleuler_d0_);
+    case AENS_SOLVER_RODAS: return (const void *)KN(aens_rodas_d1_); /* cont[] is always kept */
     }
     return nullptr;
 }

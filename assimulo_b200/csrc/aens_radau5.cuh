@@ -675,6 +675,244 @@ struct Radau5 {
     }
 };
 
+
+/* ------------------------------------------------------------------------------------------------------- */
+/* RodasODE: src/solvers/rosenbrock.py:259-465 over RODAS / ROSCOR, thirdparty/hairer/rodas_decsol.f:532-872   */
+/* (explicit problem, full Jacobian: IJOB = 1; METH = 1; IFCN = 1 with df/dx by differences; PRED = true).       */
+/* Rosenbrock 4(3): one real LU per attempt, six stages each = one RHS + one back-substitution, no Newton.      */
+/* ------------------------------------------------------------------------------------------------------- */
+namespace ro {
+/* ROCOE, METH = 1 (rodas_decsol.f:896-940); __constant__ for the same reason as dp::T */
+struct Consts {
+    double c2, c3, c4, d1, d2, d3, d4;
+    double a21, a31, a32, a41, a42, a43, a51, a52, a53, a54;
+    double c21, c31, c32, c41, c42, c43, c51, c52, c53, c54, c61, c62, c63, c64, c65, gamma;
+    double d21, d22, d23, d24, d25, d31, d32, d33, d34, d35;
+};
+static __constant__ Consts K = {
+    0.386, 0.21, 0.63, 0.2500000000000000e+00, -0.1043000000000000e+00, 0.1035000000000000e+00, -0.3620000000000023e-01,
+    0.1544000000000000e+01, 0.9466785280815826e+00, 0.2557011698983284e+00, 0.3314825187068521e+01,
+    0.2896124015972201e+01, 0.9986419139977817e+00, 0.1221224509226641e+01, 0.6019134481288629e+01,
+    0.1253708332932087e+02, -0.6878860361058950e+00,
+    -0.5668800000000000e+01, -0.2430093356833875e+01, -0.2063599157091915e+00, -0.1073529058151375e+00,
+    -0.9594562251023355e+01, -0.2047028614809616e+02, 0.7496443313967647e+01, -0.1024680431464352e+02,
+    -0.3399990352819905e+02, 0.1170890893206160e+02, 0.8083246795921522e+01, -0.7981132988064893e+01,
+    -0.3152159432874371e+02, 0.1631930543123136e+02, -0.6058818238834054e+01, 0.2500000000000000e+00,
+    0.1012623508344586e+02, -0.7487995877610167e+01, -0.3480091861555747e+02, -0.7992771707568823e+01,
+    0.1025137723295662e+01, -0.6762803392801253e+00, 0.6087714651680015e+01, 0.1643084320892478e+02,
+    0.2476722511418386e+02, -0.6594389125716872e+01};
+constexpr double uround = 1.e-16; /* rodas_decsol.f:369 */
+}  // namespace ro
+
+template <class M, bool DENSE>
+struct Rodas {
+    static constexpr bool HAS_DENSE = true; /* cont[] is cheap and the event locator needs it */
+    static constexpr int N = M::N;
+    Lane<M> L;
+    double dy1[N], fx[N], cont[4 * N];
+    double fjac[N * N], e[N * N];
+    int ip[N];
+    double h, hmaxn, hacc, erracc, told, hstep;
+    int nstep, naccpt, nrejct, njac, ndec, nfcn, nsing;
+    bool last, reject, fresh;
+
+    AENS_DEV void load_aux(const aens_args_t &, long long) {}
+    AENS_DEV void store_aux(const aens_args_t &, long long) {}
+    /* IWORK(14..19) -> statistics, rosenbrock.py:417-423 */
+    AENS_DEV void seg_end() {
+        L.st[AENS_STAT_NSTEPS] += naccpt;
+        L.st[AENS_STAT_NFCNS] += nfcn;
+        L.st[AENS_STAT_NJACS] += njac;
+        L.st[AENS_STAT_NERRFAILS] += nrejct;
+        L.st[AENS_STAT_NLUS] += ndec;
+        L.st[AENS_STAT_NSTEPSTOTAL] += nstep;
+    }
+
+    AENS_DEV void interp(double x, double *out) { /* CONTRO, rodas_decsol.f:874-882 */
+        const double s = r_div(x - told, hstep);
+#pragma unroll(N <= 4 ? 64 : 1)
+        for (int i = 0; i < N; ++i)
+            out[i] = cont[i] * (1 - s) + s * (cont[i + N] + (1 - s) * (cont[i + N * 2] + s * cont[i + N * 3]));
+    }
+
+    AENS_DEV void seg_init(const aens_args_t &a, long long idx) {
+        seg_init_events(L);
+        const double x = L.t, xend = L.tend(a);
+        const double hmax = (a.o.maxh == 0.0) ? xend - x : a.o.maxh;
+        h = a.o.inith;
+        hmaxn = dmin(dabs(hmax), dabs(xend - x));
+        if (dabs(h) <= 10.0 * ro::uround) h = 1.0e-6;
+        h = dmin(dabs(h), hmaxn);
+        reject = false; last = false; fresh = true;
+        nsing = 0; nstep = 0; naccpt = 0; nrejct = 0; njac = 0; ndec = 0; nfcn = 0;
+        hacc = 0.0; erracc = 0.0;
+        /* first SOLOUT (rodas_decsol.f:582-589): one g evaluation on a zero-length interval, rows <= x */
+        if (M::NG > 0) L.st[AENS_STAT_NSTATEFCNS] += 1;
+        while (L.gi < a.n_grid && __ldg(a.t_grid + L.gi) <= L.t) {
+#pragma unroll(N <= 4 ? 64 : 1)
+            for (int i = 0; i < N; ++i) a.dense[((long long)L.gi * N + i) * a.N + idx] = L.y[i];
+            L.gi += 1;
+        }
+    }
+
+    AENS_DEV int attempt(const aens_args_t &a, long long idx) {
+        const ro::Consts &K = ro::K;
+        const double x = L.t, xend = L.tend(a);
+        if (fresh) { /* label 1 */
+            if (nstep > a.o.maxsteps) { L.status = AENS_ST_MAXSTEPS; return AENS_R_ERROR; }
+            if (0.1 * dabs(h) <= dabs(x) * ro::uround) { L.status = AENS_ST_STEP_TOO_SMALL; return AENS_R_ERROR; }
+            if (last) return AENS_R_COMPLETE;
+            if ((x + h * 1.0001 - xend) >= 0.0) { h = xend - x; last = true; }
+            L.rhs(x, L.y, dy1);
+            nfcn += 1;
+            njac += 1;
+            if (!a.o.usejac || !M::HAS_JAC) {
+#pragma unroll(N <= 4 ? 64 : 1)
+                for (int i = 0; i < N; ++i) {
+                    const double ysafe = L.y[i];
+                    const double delt = sqrt(ro::uround * dmax(1.0e-5, dabs(ysafe)));
+                    double yp[N], fp[N];
+#pragma unroll(N <= 4 ? 64 : 1)
+                    for (int j = 0; j < N; ++j) yp[j] = (j == i) ? ysafe + delt : L.y[j];
+                    L.rhs(x, yp, fp);
+#pragma unroll(N <= 4 ? 64 : 1)
+                    for (int j = 0; j < N; ++j) AENS_A(fjac, j, i) = r_div(fp[j] - dy1[j], delt);
+                }
+            } else {
+                M::jac(x, L.y, L.sw, L.p, fjac);
+            }
+            { /* IDFX = 0: df/dx by a forward difference */
+                const double delt = sqrt(ro::uround * dmax(1.0e-5, dabs(x)));
+                double fp[N];
+                L.rhs(x + delt, L.y, fp);
+#pragma unroll(N <= 4 ? 64 : 1)
+                for (int j = 0; j < N; ++j) fx[j] = r_div(fp[j] - dy1[j], delt);
+            }
+            fresh = false;
+        }
+        /* label 2 */
+#if AENS_STRICT
+        const double fac0 = 1.0 / (h * K.gamma);
+#else
+        const double rh = r_recip(h);
+        const double fac0 = rh * (1.0 / 0.25);
+#endif
+#pragma unroll(N <= 4 ? 64 : 1)
+        for (int j = 0; j < N; ++j) {
+#pragma unroll(N <= 4 ? 64 : 1)
+            for (int i = 0; i < N; ++i) AENS_A(e, i, j) = -AENS_A(fjac, i, j);
+            AENS_A(e, j, j) = AENS_A(e, j, j) + fac0;
+        }
+        if (lu_dec<N>(e, ip) != 0) { /* label 80 */
+            nsing += 1;
+            if (nsing >= 5) { L.status = AENS_ST_RODAS_SINGULAR; return AENS_R_ERROR; }
+            h = h * 0.5;
+            reject = true; last = false;
+            return AENS_R_CONTINUE;
+        }
+        ndec += 1;
+#if AENS_STRICT
+#define AENS_HC(c) ((c) / h)
+#else
+#define AENS_HC(c) ((c) * rh)
+#endif
+        const double hc21 = AENS_HC(K.c21), hc31 = AENS_HC(K.c31), hc32 = AENS_HC(K.c32), hc41 = AENS_HC(K.c41),
+                     hc42 = AENS_HC(K.c42), hc43 = AENS_HC(K.c43), hc51 = AENS_HC(K.c51), hc52 = AENS_HC(K.c52),
+                     hc53 = AENS_HC(K.c53), hc54 = AENS_HC(K.c54), hc61 = AENS_HC(K.c61), hc62 = AENS_HC(K.c62),
+                     hc63 = AENS_HC(K.c63), hc64 = AENS_HC(K.c64), hc65 = AENS_HC(K.c65);
+#undef AENS_HC
+        const double hd1 = h * K.d1, hd2 = h * K.d2, hd3 = h * K.d3, hd4 = h * K.d4;
+        double ak1[N], ak2[N], ak3[N], ak4[N], ak5[N], ak6[N], ynew[N], dy[N];
+#pragma unroll(N <= 4 ? 64 : 1)
+        for (int i = 0; i < N; ++i) ak1[i] = dy1[i] + hd1 * fx[i];
+        lu_sol<N>(e, ak1, ip);
+#pragma unroll(N <= 4 ? 64 : 1)
+        for (int i = 0; i < N; ++i) ynew[i] = L.y[i] + K.a21 * ak1[i];
+        L.rhs(x + K.c2 * h, ynew, dy);
+#pragma unroll(N <= 4 ? 64 : 1)
+        for (int i = 0; i < N; ++i) { ak2[i] = dy[i] + hd2 * fx[i]; ak2[i] = ak2[i] + hc21 * ak1[i]; }
+        lu_sol<N>(e, ak2, ip);
+#pragma unroll(N <= 4 ? 64 : 1)
+        for (int i = 0; i < N; ++i) ynew[i] = L.y[i] + K.a31 * ak1[i] + K.a32 * ak2[i];
+        L.rhs(x + K.c3 * h, ynew, dy);
+#pragma unroll(N <= 4 ? 64 : 1)
+        for (int i = 0; i < N; ++i) { ak3[i] = dy[i] + hd3 * fx[i]; ak3[i] = ak3[i] + (hc31 * ak1[i] + hc32 * ak2[i]); }
+        lu_sol<N>(e, ak3, ip);
+#pragma unroll(N <= 4 ? 64 : 1)
+        for (int i = 0; i < N; ++i) ynew[i] = L.y[i] + K.a41 * ak1[i] + K.a42 * ak2[i] + K.a43 * ak3[i];
+        L.rhs(x + K.c4 * h, ynew, dy);
+#pragma unroll(N <= 4 ? 64 : 1)
+        for (int i = 0; i < N; ++i) {
+            ak4[i] = dy[i] + hd4 * fx[i];
+            ak4[i] = ak4[i] + (hc41 * ak1[i] + hc42 * ak2[i] + hc43 * ak3[i]);
+        }
+        lu_sol<N>(e, ak4, ip);
+#pragma unroll(N <= 4 ? 64 : 1)
+        for (int i = 0; i < N; ++i) ynew[i] = L.y[i] + K.a51 * ak1[i] + K.a52 * ak2[i] + K.a53 * ak3[i] + K.a54 * ak4[i];
+        L.rhs(x + h, ynew, dy);
+#pragma unroll(N <= 4 ? 64 : 1)
+        for (int i = 0; i < N; ++i) ak5[i] = dy[i] + (hc52 * ak2[i] + hc54 * ak4[i] + hc51 * ak1[i] + hc53 * ak3[i]);
+        lu_sol<N>(e, ak5, ip);
+#pragma unroll(N <= 4 ? 64 : 1)
+        for (int i = 0; i < N; ++i) ynew[i] = ynew[i] + ak5[i];
+        L.rhs(x + h, ynew, dy);
+#pragma unroll(N <= 4 ? 64 : 1)
+        for (int i = 0; i < N; ++i)
+            ak6[i] = dy[i] + (hc61 * ak1[i] + hc62 * ak2[i] + hc65 * ak5[i] + hc64 * ak4[i] + hc63 * ak3[i]);
+        lu_sol<N>(e, ak6, ip);
+#pragma unroll(N <= 4 ? 64 : 1)
+        for (int i = 0; i < N; ++i) ynew[i] = ynew[i] + ak6[i];
+        nfcn += 5;
+        nstep += 1;
+        double err = 0.0;
+#pragma unroll(N <= 4 ? 64 : 1)
+        for (int i = 0; i < N; ++i) {
+            const double sk = a.o.atol[i] + a.o.rtol * dmax(dabs(L.y[i]), dabs(ynew[i]));
+            const double q = r_div(ak6[i], sk);
+            err = err + q * q;
+        }
+        err = AENS_STRICT ? sqrt(err / N) : r_sqrt(err * (1.0 / N));
+        const double fac1 = r_recip(a.o.fac1), fac2 = r_recip(a.o.fac2); /* rodas_decsol.f:387-396 */
+        double fac = dmax(fac2, dmin(fac1, r_div(r_pow(err, 0.25), a.o.safe)));
+        double hnew = r_div(h, fac);
+        if (err <= 1.0) {
+            naccpt += 1;
+            if (naccpt > 1) { /* PRED: Gustafsson */
+                double facgus = r_div(r_div(hacc, h) * r_pow(r_div(err * err, erracc), 0.25), a.o.safe);
+                facgus = dmax(fac2, dmin(fac1, facgus));
+                fac = dmax(fac, facgus);
+                hnew = r_div(h, fac);
+            }
+            hacc = h;
+            erracc = dmax(1.0e-2, err);
+#pragma unroll(N <= 4 ? 64 : 1)
+            for (int i = 0; i < N; ++i) {
+                cont[i] = L.y[i];
+                cont[i + 2 * N] = K.d21 * ak1[i] + K.d22 * ak2[i] + K.d23 * ak3[i] + K.d24 * ak4[i] + K.d25 * ak5[i];
+                cont[i + 3 * N] = K.d31 * ak1[i] + K.d32 * ak2[i] + K.d33 * ak3[i] + K.d34 * ak4[i] + K.d35 * ak5[i];
+                L.y[i] = ynew[i];
+                cont[i + N] = ynew[i];
+            }
+            told = x;
+            hstep = h;
+            const double xn = x + h;
+            const int flag = aens_post_step<M, Rodas>(*this, L, a, idx, x, xn);
+            if (flag == AENS_R_EVENT) return AENS_R_EVENT;
+            if (dabs(hnew) > hmaxn) hnew = hmaxn;
+            if (reject) hnew = dmin(dabs(hnew), dabs(h));
+            reject = false;
+            h = hnew;
+            fresh = true;
+            return AENS_R_CONTINUE;
+        }
+        reject = true;
+        last = false;
+        h = hnew;
+        if (naccpt >= 1) nrejct += 1;
+        return AENS_R_CONTINUE;
+    }
+};
+
 }  // namespace aens
 
 #endif /* AENS_RADAU5_CUH */

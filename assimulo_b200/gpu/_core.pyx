@@ -82,7 +82,7 @@ STAT_NAMES = ("nsteps", "nfcns", "nerrfails", "njacs", "nlus", "nstatefcns", "ns
               "ntimeevents", "nniters", "nnfails")
 MODEL_HAS_JAC, MODEL_TIME_EVENTS = 1, 2
 SOLVER_IDS = {"ExplicitEuler": 0, "RungeKutta4": 1, "RungeKutta34": 2, "Dopri5": 3, "Radau5ODE": 4,
-              "ImplicitEuler": 5}
+              "ImplicitEuler": 5, "RodasODE": 6}
 MAX_N = 16
 
 

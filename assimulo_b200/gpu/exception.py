@@ -33,3 +33,7 @@ class Radau5Error(AssimuloException):
         self.t = t
         self.err_msg = err_msg
         AssimuloException.__init__(self, "Radau5 failed with flag %s at time %s. Message: %s" % (value, t, err_msg))
+
+
+class Rodas_Exception(AssimuloException):
+    """src/exception.py: raised by RodasODE option validation."""

@@ -19,7 +19,8 @@ There is no CPU fallback: creating the device handle raises if no CUDA device is
 """
 import numpy as np
 
-from .exception import (AssimuloException, Dopri5_Exception, Explicit_ODE_Exception, Radau_Exception)
+from .exception import (AssimuloException, Dopri5_Exception, Explicit_ODE_Exception, Radau_Exception,
+                        Rodas_Exception)
 from .problem import Batched_Explicit_Problem
 
 ARITH = {"strict": 0, "fast": 1}
@@ -664,3 +665,42 @@ class Radau5ODE(Batched_Explicit_ODE):
                  "Lower bound of the step-size ratio, default 0.2.")
     fac2 = _prop("fac2", lambda s, v: s._float_opt("fac2", v, "The attribute 'fac2' must be an integer or float."),
                  "Upper bound of the step-size ratio, default 8.")
+
+
+class RodasODE(Batched_Explicit_ODE):
+    """Rosenbrock method of order (3)4 with step-size control and continuous output -- RODAS by Hairer & Wanner
+    (src/solvers/rosenbrock.py:259-465 over thirdparty/hairer/rodas_decsol.f).  One LU decomposition per attempt,
+    six stages, no Newton iteration; analytic or finite-difference Jacobian, df/dt by a forward difference."""
+    _solver_name = "RodasODE"
+    _exc = Rodas_Exception
+
+    def __init__(self, problem, **kw):
+        Batched_Explicit_ODE.__init__(self, problem, **kw)
+        self.options.update(inith=0.01, fac1=0.2, fac2=6.0, maxh=np.inf, safe=0.9, atol=1.0e-6 * np.ones(self._leny),
+                            rtol=1.0e-6, usejac=bool(problem.has_jac), maxsteps=10000)
+        self.supports.update(report_continuously=True, interpolated_output=True, state_events=True)
+
+    def _set_usejac(self, v):
+        self.options["usejac"] = bool(v)
+
+    def _set_maxh(self, v):
+        try:
+            self.options["maxh"] = float(v)
+        except (ValueError, TypeError):
+            raise Rodas_Exception("Maximal stepsize must be a (scalar) float.")
+        if self.options["maxh"] < 0:
+            raise Rodas_Exception("Maximal stepsize must be a positiv (scalar) float.")
+
+    atol = _prop("atol", Batched_Explicit_ODE._set_atol_common, "Absolute tolerance(s), default 1e-6.")
+    rtol = _prop("rtol", Batched_Explicit_ODE._set_rtol_common, "Relative tolerance, default 1e-6.")
+    maxsteps = _prop("maxsteps", Batched_Explicit_ODE._set_maxsteps_common, "Maximum number of steps, default 10000.")
+    usejac = _prop("usejac", _set_usejac, "Use the model's analytic Jacobian instead of finite differences.")
+    maxh = _prop("maxh", _set_maxh, "Maximal step-size, default inf.")
+    inith = _prop("inith", lambda s, v: s._float_opt("inith", v, "The initial step must be an integer or float."),
+                  "Initial step-size, default 0.01.")
+    fac1 = _prop("fac1", lambda s, v: s._float_opt("fac1", v, "The fac1 must be an integer or float."),
+                 "Lower bound of the step-size ratio, default 0.2.")
+    fac2 = _prop("fac2", lambda s, v: s._float_opt("fac2", v, "The fac2 must be an integer or float."),
+                 "Upper bound of the step-size ratio, default 6.")
+    safe = _prop("safe", lambda s, v: s._float_opt("safe", v, "The safe must be an integer or float."),
+                 "Safety factor, default 0.9.")

@@ -51,20 +51,22 @@ extern "C" {
 #define AENS_ERR_STATE (-4)          /* call order violated (e.g. simulate before set_ensemble) */
 #define AENS_ERR_UNSUPPORTED (-5)    /* model/solver combination not available */
 
-/* solver ids (the five Explicit_ODE subclasses of BASELINE.json + ImplicitEuler) */
+/* solver ids (the five Explicit_ODE subclasses of BASELINE.json + ImplicitEuler and RodasODE, SURVEY 8f-2,3) */
 #define AENS_SOLVER_EULER 0          /* src/solvers/euler.pyx:485 ExplicitEuler */
 #define AENS_SOLVER_RK4 1            /* src/solvers/runge_kutta.py:746 RungeKutta4 */
 #define AENS_SOLVER_RK34 2           /* src/solvers/runge_kutta.py:430 RungeKutta34 */
 #define AENS_SOLVER_DOPRI5 3         /* src/solvers/runge_kutta.py:26 Dopri5 */
 #define AENS_SOLVER_RADAU5 4         /* src/solvers/radau5.py:69 Radau5ODE */
 #define AENS_SOLVER_IMPLEULER 5      /* src/solvers/euler.pyx:29 ImplicitEuler */
-#define AENS_NSOLVERS 6
+#define AENS_SOLVER_RODAS 6          /* src/solvers/rosenbrock.py:259 RodasODE */
+#define AENS_NSOLVERS 7
 
 /* per-member status written by aens_simulate (aens_get_final) */
 #define AENS_ST_COMPLETE 0           /* reached tfinal (ID_PY_COMPLETE) */
 #define AENS_ST_TERMINATED 1         /* handle_event asked to stop (TerminateSimulation) */
 #define AENS_ST_MAXSTEPS (-2)        /* DOPRI5 IDID=-2 / RK34 'Final time not reached' */
 #define AENS_ST_STEP_TOO_SMALL (-3)  /* DOPRI5 IDID=-3 */
+#define AENS_ST_RODAS_SINGULAR (-4)  /* RODAS IDID=-4: matrix repeatedly singular */
 #define AENS_ST_RADAU_NMAX (-5)      /* RADAU_ERROR_NMAX_TOO_SMALL */
 #define AENS_ST_RADAU_STEP_TOO_SMALL (-6)
 #define AENS_ST_RADAU_SINGULAR (-7)   /* also: singular Newton matrix in ImplicitEuler (numpy LinAlgError) */
@@ -98,7 +100,7 @@ typedef struct {
     double rtol;         /* scalar, broadcast to n (runge_kutta.py:172, radau5.py:374) */
     double atol[AENS_MAX_N];
     double h;            /* ExplicitEuler / RungeKutta4 fixed step (0.01) */
-    double inith;        /* Dopri5: 0 => HINIT; RungeKutta34, Radau5ODE: 0.01 */
+    double inith;        /* Dopri5: 0 => HINIT; RungeKutta34, Radau5ODE, RodasODE: 0.01 */
     double maxh;         /* 0 => unset (Dopri5: inf; Radau5ODE: tfinal - t) */
     double safe, fac1, fac2, beta;
     double thet, fnewt /* 0 => automatic */, quot1, quot2;

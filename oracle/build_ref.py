@@ -12,6 +12,8 @@ What it does (recipe: SURVEY.md App. B, which restates /root/reference/setup.py:
 * cythonizes + compiles ``ode, problem, support, explicit_ode (+ode_event_locator.c), implicit_ode,
   solvers/euler`` and ``lib/radau5ode (+radau5.c, radau5_io.c, no SuperLU)`` with
   ``-O2 -fno-strict-aliasing`` (setup.py:564);
+* ``oracle/rodas_c.c`` + ``oracle/rodas_f2py_shim.py`` do the same for RODAS (thirdparty/hairer/rodas_decsol.f ->
+  ``assimulo/lib/rodas.py``), so that ``rosenbrock.py::RodasODE`` runs unmodified;
 * the Fortran DOPRI5 core (thirdparty/hairer/dopri5.f) cannot be built here (no Fortran compiler, no
   numpy.distutils): ``oracle/dopri5_c.c`` -- our C restatement of that file -- is compiled to
   ``oracle/_ref/libdopri5_c.so`` and ``oracle/dopri5_f2py_shim.py`` is installed as
@@ -49,14 +51,23 @@ def stage(ref):
     r5 = os.path.join(ref, "thirdparty", "radau5")
     _copy(os.listdir(r5), r5, os.path.join(pkg, "thirdparty", "radau5"))
     open(os.path.join(pkg, "thirdparty", "__init__.py"), "a").close()
-    # our f2py stand-in for the Fortran module (NOT reference code)
+    # our f2py stand-ins for the Fortran modules (NOT reference code)
     shutil.copy2(os.path.join(HERE, "dopri5_f2py_shim.py"), os.path.join(pkg, "lib", "dopri5.py"))
+    shutil.copy2(os.path.join(HERE, "rodas_f2py_shim.py"), os.path.join(pkg, "lib", "rodas.py"))
 
 
 def build_dopri5_c():
     so = os.path.join(OUT, "libdopri5_c.so")
     cmd = ["gcc", "-O2", "-ffp-contract=off", "-fno-strict-aliasing", "-fPIC", "-shared",
            os.path.join(HERE, "dopri5_c.c"), "-o", so, "-lm"]
+    subprocess.check_call(cmd)
+    return so
+
+
+def build_rodas_c():
+    so = os.path.join(OUT, "librodas_c.so")
+    cmd = ["gcc", "-O2", "-ffp-contract=off", "-fno-strict-aliasing", "-fPIC", "-shared",
+           os.path.join(HERE, "rodas_c.c"), "-o", so, "-lm"]
     subprocess.check_call(cmd)
     return so
 
@@ -121,7 +132,9 @@ def main(argv=None):
     if is_built() and not a.force:
         # refresh only our own pieces (cheap)
         build_dopri5_c()
+        build_rodas_c()
         shutil.copy2(os.path.join(HERE, "dopri5_f2py_shim.py"), os.path.join(OUT, "assimulo", "lib", "dopri5.py"))
+        shutil.copy2(os.path.join(HERE, "rodas_f2py_shim.py"), os.path.join(OUT, "assimulo", "lib", "rodas.py"))
         print("oracle/_ref already built")
         return 0
     if not os.path.isdir(a.reference):
@@ -130,6 +143,7 @@ def main(argv=None):
     os.makedirs(OUT, exist_ok=True)
     stage(a.reference)
     build_dopri5_c()
+    build_rodas_c()
     build_cython()
     shutil.rmtree(os.path.join(OUT, "_build_tmp"), ignore_errors=True)
     shutil.rmtree(os.path.join(OUT, "build"), ignore_errors=True)

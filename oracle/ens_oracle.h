@@ -13,7 +13,7 @@ extern "C" {
 #define ORA_MAX_N 16
 #define ORA_MAX_G 8
 
-enum { ORA_EULER = 0, ORA_RK4 = 1, ORA_RK34 = 2, ORA_DOPRI5 = 3, ORA_RADAU5 = 4, ORA_IMPLEULER = 5 };
+enum { ORA_EULER = 0, ORA_RK4 = 1, ORA_RK34 = 2, ORA_DOPRI5 = 3, ORA_RADAU5 = 4, ORA_IMPLEULER = 5, ORA_RODAS = 6 };
 enum { ORA_VDP = 0, ORA_BALL = 1, ORA_ROBERTSON = 2, ORA_GYRO = 3, ORA_LINEAR = 4, ORA_LINEAR_EV = 5,
        ORA_EXTENDED = 6, ORA_TIME_EV = 7 };
 

@@ -13,7 +13,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB = os.path.join(HERE, "libens_oracle.so")
 
 MAX_N = 16
-SOLVERS = {"ExplicitEuler": 0, "RungeKutta4": 1, "RungeKutta34": 2, "Dopri5": 3, "Radau5ODE": 4, "ImplicitEuler": 5}
+SOLVERS = {"ExplicitEuler": 0, "RungeKutta4": 1, "RungeKutta34": 2, "Dopri5": 3, "Radau5ODE": 4, "ImplicitEuler": 5,
+           "RodasODE": 6}
 MODELS = {"vdp": 0, "ball": 1, "robertson": 2, "gyro": 3, "linear": 4, "linear_ev": 5, "extended": 6, "time_ev": 7}
 STATS = ["nsteps", "nfcns", "nerrfails", "njacs", "nlus", "nstatefcns", "nstateevents", "nstepstotal",
          "ntimeevents", "nniters", "nnfails"]

@@ -148,6 +148,40 @@ def implicit_euler_cases():
     save("impleuler_linear_ev", **pack_ie(res))
 
 
+def rodas_cases():
+    """RodasODE (src/solvers/rosenbrock.py:259-465).  The reference's class runs over oracle/rodas_c.c, our C
+    restatement of the Fortran RODAS core (no Fortran compiler here): these vectors pin the ensemble oracle and the
+    GPU path to that pair, and the pair itself to the reference's one known answer (VdP mu = 1e6)."""
+    N = 4096
+    idx = np.arange(0, N, 256)
+    y0, p = cases.vdp_sweep(N, idx)
+    for tag, usejac in (("jac", True), ("fd", False)):
+        res = [run_member(ref_models.vdp(float(mu)), "RodasODE", 2.0, rtol=1e-6, atol=1e-6, usejac=usejac) for mu in p[:, 0]]
+        save("rodas_vdp_" + tag, N=N, idx=idx, mu=p[:, 0], **pack(res))
+    res = [run_member(ref_models.vdp(1e6), "RodasODE", 2.0, rtol=1e-4, atol=1e-4)]   # test_rosenbrock.py:83-91
+    save("rodas_vdp_mu1e6", **pack(res))
+    N = 1 << 18
+    idx = np.arange(0, N, N // 8)
+    y0, p = cases.robertson_sweep(N, idx)
+    res = [run_member(ref_models.robertson(*[float(v) for v in pk], with_jac=True), "RodasODE", 40.0,
+                      rtol=1e-6, atol=cases.ROBERTSON_ATOL) for pk in p]
+    save("rodas_robertson", N=N, idx=idx, p=p, **pack(res))
+    N = 1 << 20
+    idx = np.arange(0, N, N // 8)
+    y0, p, sw0 = cases.ball_sweep(N, idx)
+    res = [run_member(ref_models.ball(float(h0)), "RodasODE", 3.0, rtol=1e-6, atol=1e-6) for h0 in y0[:, 0]]
+    save("rodas_ball", N=N, idx=idx, h0=y0[:, 0], **pack(res))
+    grid = np.linspace(0.0, 3.0, 31)[1:]
+    r = run_member(ref_models.ball(2.0), "RodasODE", 3.0, ncp=30, report_continuously=True, rtol=1e-6, atol=1e-6)
+    t, y = r["t_sol"], r["y_sol"]
+    dense = np.full((len(grid), 2), np.nan)
+    for k, tg in enumerate(grid):
+        hit = np.nonzero(t == tg)[0]
+        if len(hit):
+            dense[k] = y[hit[0]]
+    save("ball_dense_rodasode", grid=grid, dense=dense, **pack([r]))
+
+
 def pack_ie(results):
     out = pack(results)
     for k in ("nniters", "nnfails"):
@@ -161,8 +195,11 @@ def main():
         return time_event_cases()
     if len(sys.argv) > 1 and sys.argv[1] == "implicit_euler":
         return implicit_euler_cases()
+    if len(sys.argv) > 1 and sys.argv[1] == "rodas":
+        return rodas_cases()
     time_event_cases()
     implicit_euler_cases()
+    rodas_cases()
     # ---- cfg 1: Dopri5 VdP sweep (subset of the N=4096 law) --------------------------------------
     N = 4096
     idx = np.arange(0, N, 64)

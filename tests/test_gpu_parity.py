@@ -416,3 +416,76 @@ def test_implicit_euler_solver_class():
     o = O.simulate("vdp", "ImplicitEuler", y0, mu, tf=2.0, h=1e-3, usejac=1)
     assert len(t) == 5 and rel_err(y[-1], o["y"]) <= 1e-10
     assert sim.statistics["nniters"] == int(o["stats"]["nniters"].sum()) and sim.statistics["nsteps"] == 64 * 2001
+
+
+# ---------------------------------------------------------------------------------------------------------
+# RodasODE
+# ---------------------------------------------------------------------------------------------------------
+RODAS_KEYS = ("nsteps", "nfcns", "nerrfails", "njacs", "nlus")
+
+
+@pytest.mark.parametrize("usejac", [1, 0])
+@pytest.mark.parametrize("arith", ["strict", "fast"])
+def test_rodas_vdp_sweep(usejac, arith):
+    N = 2048
+    y0, p = cases.vdp_sweep(N)
+    o = O.simulate("vdp", "RodasODE", y0, p, tf=2.0, rtol=RTOL, atol=1e-6, usejac=usejac)
+    g = gpu("vdp", "RodasODE", y0, p, tf=2.0, rtol=RTOL, atol=1e-6, usejac=usejac, arith=arith)
+    assert (g["status"] == 0).all() and np.array_equal(g["t"], o["t"])
+    # strict arithmetic reproduces every operation except libm's pow (err ** 0.25 in the controller: device and glibc
+    # pow differ by an ulp now and then, hence h, hence the state in its last bits).  With an analytic Jacobian that
+    # stays at 1e-13; a finite-difference Jacobian divides such last-bit differences by delt ~ 1e-8 and a Rosenbrock
+    # method uses J in the solution itself (not only for convergence like Newton), so there the bound is rtol.
+    strict_tol = 1e-10 if usejac else RTOL
+    assert rel_err(g["y"], o["y"]) <= (strict_tol if arith == "strict" else 10 * RTOL)
+    assert steps_within(g, o)
+    if arith == "strict" and usejac:
+        for k in RODAS_KEYS:
+            assert np.array_equal(g["stats"][k], o["stats"][k]), k
+    elif arith == "strict":
+        assert np.abs(g["stats"]["nsteps"].astype(int) - o["stats"]["nsteps"]).max() <= 2
+    gold = golden("rodas_vdp_" + ("jac" if usejac else "fd"))
+    y0g, pg = cases.vdp_sweep(int(gold["N"]), gold["idx"])
+    gg = gpu("vdp", "RodasODE", y0g, pg, tf=2.0, rtol=RTOL, atol=1e-6, usejac=usejac, arith=arith)
+    assert rel_err(gg["y"], gold["y"]) <= (strict_tol if arith == "strict" else 10 * RTOL)
+
+
+@pytest.mark.parametrize("arith", ["strict", "fast"])
+def test_rodas_stiff_events_dense(arith):
+    # the reference's known answer (tests/solvers/test_rosenbrock.py:83-91)
+    g = gpu("vdp", "RodasODE", [[2.0, -0.6]], [[1e6]], tf=2.0, rtol=1e-4, atol=1e-4, usejac=1, arith=arith)
+    assert g["status"][0] == 0 and abs(g["y"][0, 0] - 1.7061680350) < 1e-4
+    # Robertson, 2^10 members
+    N = 1024
+    y0, p = cases.robertson_sweep(N)
+    o = O.simulate("robertson", "RodasODE", y0, p, tf=40.0, rtol=1e-6, atol=cases.ROBERTSON_ATOL, usejac=1)
+    g = gpu("robertson", "RodasODE", y0, p, tf=40.0, rtol=1e-6, atol=np.array(cases.ROBERTSON_ATOL), usejac=1, arith=arith)
+    assert (g["status"] == 0).all() and rel_err(g["y"], o["y"]) <= 1e-5 and steps_within(g, o)
+    assert np.max(np.abs(g["y"].sum(axis=1) - 1.0)) < 1e-9
+    # bouncing ball: state events through CONTRO
+    y0, p, sw0 = cases.ball_sweep(512)
+    o = O.simulate("ball", "RodasODE", y0, p, sw0, tf=3.0, max_ev=24, rtol=1e-6, atol=1e-6)
+    g = gpu("ball", "RodasODE", y0, p, sw0, tf=3.0, rtol=1e-6, atol=1e-6, arith=arith)
+    assert (g["status"] == 0).all() and np.array_equal(g["nev"], o["stats"]["nstateevents"])
+    m = np.isfinite(o["ev_t"])
+    assert np.max(np.abs(g["ev_t"][m] - o["ev_t"][m])) < 1e-9 and rel_err(g["y"], o["y"]) <= 1e-5
+    # dense rows
+    grid = np.linspace(0, 2, 41)[1:]
+    y0v, pv = cases.vdp_sweep(300)
+    o = O.simulate("vdp", "RodasODE", y0v, pv, tf=2.0, t_grid=grid, usejac=1)
+    g = gpu("vdp", "RodasODE", y0v, pv, tf=2.0, t_grid=grid, usejac=1, arith=arith)
+    assert np.nanmax(np.abs(g["dense"] - o["dense"])) <= (1e-9 if arith == "strict" else 1e-4) and not np.isnan(g["dense"]).any()
+
+
+def test_rodas_solver_class():
+    from assimulo_b200.gpu import Batched_Explicit_Problem, RodasODE, Rodas_Exception
+    y0, mu = cases.vdp_sweep(64)
+    sim = RodasODE(Batched_Explicit_Problem(model="vdp", y0=y0, p0=mu))
+    assert sim.usejac and sim.maxsteps == 10000 and sim.fac2 == 6.0 and sim.inith == 0.01
+    with pytest.raises(Rodas_Exception):
+        sim.maxh = -1.0
+    t, y = sim.simulate(2.0, 4)
+    o = O.simulate("vdp", "RodasODE", y0, mu, tf=2.0, usejac=1)
+    assert len(t) == 5 and rel_err(y[-1], o["y"]) <= 1e-5
+    assert abs(sim.statistics["nsteps"] - int(o["stats"]["nsteps"].sum())) <= 0.02 * o["stats"]["nsteps"].sum()
+    assert sim.statistics["nlus"] > 0 and sim.statistics["njacs"] > 0
