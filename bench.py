@@ -282,6 +282,10 @@ def run_other_configs(device, peak_tflops, hbm_gbs):
     y0, p = cases.robertson_sweep(1 << 18)
     run("cfg4 Radau5ODE Robertson, analytic Jacobian", "robertson", "Radau5ODE", y0, p, None, 40.0, 1040,
         rtol=1e-6, atol=np.array(cases.ROBERTSON_ATOL), usejac=1)
+    # the same ensemble with RodasODE: ~420 flops per accepted step by the same counting convention
+    # (6 x (RHS + back-substitution), LU, Jacobian, df/dt difference, stage combinations, CONTRO coefficients)
+    run("cfg4' RodasODE Robertson, analytic Jacobian", "robertson", "RodasODE", y0, p, None, 40.0, 420,
+        rtol=1e-6, atol=np.array(cases.ROBERTSON_ATOL), usejac=1)
     y0, p = cases.gyro_sweep(1 << 22)
     run("cfg5 Dopri5 gyro (12 states), dense output every 1e-3", "gyro", "Dopri5", y0, p, None, 0.1,
         81 * 12 + 6 * 39 + 20, t_grid=np.linspace(0.0, 0.1, 101)[1:], rtol=1e-8, atol=1e-8)

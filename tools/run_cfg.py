@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Run ONE BASELINE config a few times (for ncu captures):  python tools/run_cfg.py {rk4|rk34|dopri5|ball|radau|gyro|gyrodense} [reps]"""
+"""Run ONE BASELINE config a few times (for ncu captures):  python tools/run_cfg.py {rk4|rk34|dopri5|ball|radau|rodas|gyro|gyrodense} [reps]"""
 import os, sys
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -18,6 +18,9 @@ if which in ("rk4", "rk34", "dopri5"):
                     "dopri5": ("Dopri5", dict(rtol=1e-6, atol=1e-6))}[which]
 elif which == "ball":
     y0, p, sw0 = cases.ball_sweep(N); model = "ball"; tf = 3.0; solver, opts = "Dopri5", dict(rtol=1e-6, atol=1e-6)
+elif which == "rodas":
+    y0, p = cases.robertson_sweep(1 << 18); sw0 = None; model = "robertson"; tf = 40.0
+    solver, opts = "RodasODE", dict(rtol=1e-6, atol=np.array(cases.ROBERTSON_ATOL), usejac=1)
 elif which == "radau":
     y0, p = cases.robertson_sweep(1 << 18); sw0 = None; model = "robertson"; tf = 40.0
     solver, opts = "Radau5ODE", dict(rtol=1e-6, atol=np.array(cases.ROBERTSON_ATOL), usejac=1)
