@@ -44,6 +44,9 @@ typedef struct {
     unsigned char *out_sw;    /* [N][n_sw] */
     int *out_status;          /* [N] */
     double tf;
+    /* Row reduction mode (aens_set_row_reduction): when red != NULL the dense-output rows are not stored but added
+     * to per-warp partial records red[warp][row][5 n + 1] (aens_reduce_grid in aens_device.cuh). */
+    double *red;
     /* step-size-controller constants of the FAST Dopri5 build in the log2 domain, computed once on the host
      * (aens_abi.cu, fill_ctl) so that the kernel reads them as constant-bank operands instead of holding them in
      * registers: [0] (0.2-0.75 beta)/2  [1] beta/2  [2] -lg2 safe  [3] -lg2 fac1  [4] -lg2 fac2

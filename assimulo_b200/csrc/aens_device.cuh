@@ -288,8 +288,146 @@ AENS_DEV int aens_locate(S &s, Lane<M> &L, double t_low, double &t_high, double 
 
 /* report_solution(): rows `while grid[k] <= t` from the interpolant of the last step (explicit_ode.pyx:308-318).
  * Row layout [k][component][member]: lanes of a warp that emit the same row store 256 contiguous bytes. */
+/* Row reduction mode (ensemble outputs without materialising [rows][n][N] in HBM).  Instead of storing
+ * its row values a lane hands them to its warp through a shared tile; the lanes of the warp that arrived here
+ * together add them to the WARP's private partial record of that row,
+ *     rec[row] = { pivot[n], sum(v - pivot)[n], sum((v - pivot)^2)[n], min[n], max[n], count },
+ * with plain loads and stores (the records of the ~10 rows a warp is working on stay in L1/L2); aens_combine_rows_k
+ * merges the partials of all warps after the launch.  The lanes of a warp reach this point in arbitrary subsets
+ * (others are rejecting a step, locating an event, ...), and independent thread scheduling may interleave two such
+ * subsets, so a per-warp lock in shared memory serialises them. */
+AENS_DEV int *aens_red_lock() {
+    __shared__ int lock[AENS_BLOCK / 32];
+    return lock;
+}
+
+template <class M, class S>
+AENS_DEV void aens_reduce_grid(S &s, Lane<M> &L, const aens_args_t &a, double t) {
+    constexpr int N = M::N, REC = 5 * N + 1;
+    /* rows handled per pass: a step usually crosses several rows, and up to 32 (row, component) items give every
+     * lane of the warp one column to accumulate in the loop below; 33-double pitch = conflict-free both ways */
+    constexpr int RS = (32 / N) > 8 ? 8 : (32 / N), ITEMS = RS * N;
+    __shared__ double tile[AENS_BLOCK / 32][ITEMS][33];
+    __shared__ unsigned tmask[AENS_BLOCK / 32][RS];
+    const unsigned lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
+    const unsigned mask = __activemask();
+    bool pend = L.gi < a.n_grid && __ldg(a.t_grid + L.gi) <= t;
+    if (!__any_sync(mask, pend)) return;
+    const int nact = __popc(mask), rank = __popc(mask & ((1u << lane) - 1u));
+    int *lk = aens_red_lock() + w;
+    if (rank == 0) {
+        while (atomicCAS(lk, 0, 1) != 0) __nanosleep(40);
+        __threadfence_block();
+    }
+    __syncwarp(mask);
+    double *base = a.red + (long long)(blockIdx.x * (AENS_BLOCK / 32) + w) * a.n_grid * REC;
+    /* one column of the tile (the values the lanes in mm hold for one row and component) into (sm, q, mn, mx);
+     * two interleaved partial sums halve the dependent fp64 chains, min and max share one compare per pair.
+     * (Testing the values against the record's bounds first and updating the extrema in a rare second scan was
+     * slower: parameter sweeps are sorted, so nearly every batch of members moves an extremum.) */
+    auto accumulate = [](const double *col, unsigned mm, double K, double &sm, double &q, double &mn, double &mx) {
+        if (mm == 0xffffffffu) {
+            double s1 = 0.0, q1 = 0.0;
+#pragma unroll
+            for (int j = 0; j < 32; j += 2) {
+                const double v0 = col[j], v1 = col[j + 1], d0 = v0 - K, d1 = v1 - K;
+                sm += d0; s1 += d1;
+                q = fma(d0, d0, q); q1 = fma(d1, d1, q1);
+                const double lo = v0 < v1 ? v0 : v1, hi = v0 < v1 ? v1 : v0;
+                mn = lo < mn ? lo : mn;
+                mx = hi > mx ? hi : mx;
+            }
+            sm += s1; q += q1;
+        } else {
+            for (unsigned b = mm; b; b &= b - 1u) {
+                const double v = col[__ffs(b) - 1], d = v - K;
+                sm += d;
+                q = fma(d, d, q);
+                mn = v < mn ? v : mn;
+                mx = v > mx ? v : mx;
+            }
+        }
+    };
+    for (;;) {
+        const int r0 = __reduce_min_sync(mask, pend ? L.gi : 0x7fffffff);
+        if (r0 == 0x7fffffff) break;
+        /* enough lanes for one item each: the item's record is loaded before the interpolation hides the latency,
+         * and the lane of component 0 also owns the row's count */
+        const bool one_each = nact >= ITEMS;
+        const int k1 = rank / N, c1 = rank - k1 * N;
+        const bool own = one_each && rank < ITEMS && r0 + k1 < a.n_grid;
+        double K = 0.0, sm = 0.0, q = 0.0, mn = 0.0, mx = 0.0, cnt0 = 0.0;
+        double *rec1 = base + (long long)(r0 + k1) * REC;
+        if (own) {
+            cnt0 = rec1[5 * N];
+            K = rec1[c1]; sm = rec1[N + c1]; q = rec1[2 * N + c1]; mn = rec1[3 * N + c1]; mx = rec1[4 * N + c1];
+        }
+#pragma unroll
+        for (int k = 0; k < RS; ++k) {
+            const bool mine = pend && L.gi == r0 + k;
+            const unsigned mm = __ballot_sync(mask, mine);
+            if (rank == 0) tmask[w][k] = mm;
+            if (mine) {
+                double out[N];
+                s.interp(__ldg(a.t_grid + L.gi), out);
+#pragma unroll
+                for (int i = 0; i < N; ++i) tile[w][k * N + i][lane] = out[i];
+                L.gi += 1;
+                pend = L.gi < a.n_grid && __ldg(a.t_grid + L.gi) <= t;
+            }
+        }
+        __syncwarp(mask);
+        if (one_each) {
+            const unsigned mm = own ? tmask[w][k1] : 0u;
+            if (mm) {
+                const double *col = tile[w][rank];
+                if (cnt0 == 0.0) {
+                    K = col[__ffs(mm) - 1];
+                    if (!(dabs(K) < 1.0e300)) K = 0.0; /* a non-finite first value must not become the pivot */
+                    sm = 0.0; q = 0.0; mn = 1.0e300 * 1.0e300; mx = -1.0e300 * 1.0e300;
+                }
+                accumulate(col, mm, K, sm, q, mn, mx);
+                rec1[c1] = K; rec1[N + c1] = sm; rec1[2 * N + c1] = q; rec1[3 * N + c1] = mn; rec1[4 * N + c1] = mx;
+                if (c1 == 0) rec1[5 * N] = cnt0 + (double)__popc(mm);
+            }
+            __syncwarp(mask);
+            continue;
+        }
+        for (int it = rank; it < ITEMS; it += nact) {
+            const int k = it / N, c = it - k * N;
+            const unsigned mm = tmask[w][k];
+            if (mm == 0u) continue;
+            double *rec = base + (long long)(r0 + k) * REC;
+            const double *col = tile[w][it];
+            if (rec[5 * N] == 0.0) {
+                K = col[__ffs(mm) - 1];
+                if (!(dabs(K) < 1.0e300)) K = 0.0;
+                sm = 0.0; q = 0.0; mn = 1.0e300 * 1.0e300; mx = -1.0e300 * 1.0e300;
+            } else {
+                K = rec[c]; sm = rec[N + c]; q = rec[2 * N + c]; mn = rec[3 * N + c]; mx = rec[4 * N + c];
+            }
+            accumulate(col, mm, K, sm, q, mn, mx);
+            rec[c] = K; rec[N + c] = sm; rec[2 * N + c] = q; rec[3 * N + c] = mn; rec[4 * N + c] = mx;
+        }
+        __syncwarp(mask); /* every item has read its row's count and the tile */
+        for (int k = rank; k < RS; k += nact) {
+            const unsigned mm = tmask[w][k];
+            if (mm) base[(long long)(r0 + k) * REC + 5 * N] += (double)__popc(mm);
+        }
+        __syncwarp(mask);
+    }
+    if (rank == 0) {
+        __threadfence_block();
+        atomicExch(lk, 0);
+    }
+}
+
 template <class M, class S>
 AENS_DEV void aens_emit_grid(S &s, Lane<M> &L, const aens_args_t &a, long long idx, double t) {
+    if constexpr (S::REDUCE) { /* the d2 kernels: rows are reduced over the ensemble, not stored */
+        aens_reduce_grid<M, S>(s, L, a, t);
+        return;
+    }
     while (L.gi < a.n_grid && __ldg(a.t_grid + L.gi) <= t) {
         double out[M::N];
         s.interp(__ldg(a.t_grid + L.gi), out);
@@ -334,9 +472,10 @@ AENS_DEV int aens_post_step(S &s, Lane<M> &L, const aens_args_t &a, long long id
 template <int N> AENS_DEV int lu_dec(double *a, int *ip);
 template <int N> AENS_DEV void lu_sol(const double *a, double *b, const int *ip);
 
-template <class M, bool DENSE, bool IMPL = false>
+template <class M, int DENSE, bool IMPL = false>
 struct Euler {
-    static constexpr bool HAS_DENSE = DENSE;
+    static constexpr bool HAS_DENSE = DENSE != 0;
+    static constexpr bool REDUCE = DENSE == 2;
     static constexpr int N = M::N;
     Lane<M> L;
     double h, inith;          /* inith = _inith: remainder of a grid step cut by an event */
@@ -508,15 +647,16 @@ struct Euler {
         return inner ? AENS_R_CONTINUE : AENS_R_COMPLETE;
     }
 };
-template <class M, bool DENSE>
+template <class M, int DENSE>
 using ImplEuler = Euler<M, DENSE, true>;
 
 /* ------------------------------------------------------------------------------------------------------- */
 /* RungeKutta4, src/solvers/runge_kutta.py:839-862 (no events, no dense output in the reference)            */
 /* ------------------------------------------------------------------------------------------------------- */
-template <class M, bool DENSE>
+template <class M, int DENSE>
 struct RK4 {
     static constexpr bool HAS_DENSE = false;
+    static constexpr bool REDUCE = false;
     static constexpr int N = M::N;
     Lane<M> L;
     double h;
@@ -562,9 +702,10 @@ struct RK4 {
 /* ------------------------------------------------------------------------------------------------------- */
 /* RungeKutta34, src/solvers/runge_kutta.py:618-723                                                          */
 /* ------------------------------------------------------------------------------------------------------- */
-template <class M, bool DENSE>
+template <class M, int DENSE>
 struct RK34 {
-    static constexpr bool HAS_DENSE = DENSE;
+    static constexpr bool HAS_DENSE = DENSE != 0;
+    static constexpr bool REDUCE = DENSE == 2;
     static constexpr int N = M::N;
     Lane<M> L;
     double h, Y1[N];
@@ -694,9 +835,10 @@ __host__ __device__ constexpr float lg2_int(int n) {
            n == 14 ? 3.8073549221f : n == 15 ? 3.9068905956f : 4.f;
 }
 
-template <class M, bool DENSE>
+template <class M, int DENSE>
 struct Dopri5 {
-    static constexpr bool HAS_DENSE = DENSE;
+    static constexpr bool HAS_DENSE = DENSE != 0;
+    static constexpr bool REDUCE = DENSE == 2;
     static constexpr int N = M::N;
     /* FAST build, small systems: the stage arguments are accumulated incrementally (see attempt_fast) */
     static constexpr bool INCREMENTAL = (N <= 4);
@@ -1182,6 +1324,10 @@ __device__ __forceinline__ void aens_run(const aens_args_t &a) {
     const int lane = threadIdx.x & 31;
     const double eps = 2.220446049250313e-16 * 100; /* explicit_ode.pyx:184 */
     S s;
+    if constexpr (S::REDUCE) { /* the per-warp locks of aens_reduce_grid */
+        if (threadIdx.x < AENS_BLOCK / 32) aens::aens_red_lock()[threadIdx.x] = 0;
+        __syncthreads();
+    }
     long long idx = -1;
     int phase = PH_IDLE;
     bool te_at_end = false; /* models with time events: the current segment ends on a time event */
@@ -1299,6 +1445,8 @@ __device__ __forceinline__ void aens_run(const aens_args_t &a) {
     }
 }
 
+/* DENSE: 0 = no interpolation data kept, 1 = dense output (grid rows stored, event location), 2 = as 1 but the grid
+ * rows are reduced over the ensemble (aens_reduce_grid) */
 #define AENS_DEFINE_KERNEL(NAME, STEPPER, MODEL, DENSE, MINBLOCKS)                                   \
     extern "C" __global__ void __launch_bounds__(AENS_BLOCK, MINBLOCKS) NAME(const aens_args_t a) {  \
         aens_run<aens::STEPPER<MODEL, DENSE>, MODEL>(a);                                             \

@@ -43,6 +43,13 @@ AENS_DEFINE_KERNEL(KN(aens_dopri5_d1_), Dopri5, KM, true, AENS_MB_DOPRI5)
 AENS_DEFINE_KERNEL(KN(aens_radau5_d1_), Radau5, KM, true, AENS_MB_RADAU5)
 AENS_DEFINE_KERNEL(KN(aens_impleuler_d1_), ImplEuler, KM, true, AENS_MB_EULER)
 AENS_DEFINE_KERNEL(KN(aens_rodas_d1_), Rodas, KM, true, AENS_MB_RADAU5)
+/* row reduction mode (aens_set_row_reduction): the grid rows are reduced over the ensemble inside the kernel */
+AENS_DEFINE_KERNEL(KN(aens_euler_d2_), Euler, KM, 2, AENS_MB_EULER)
+AENS_DEFINE_KERNEL(KN(aens_rk34_d2_), RK34, KM, 2, AENS_MB_RK34)
+AENS_DEFINE_KERNEL(KN(aens_dopri5_d2_), Dopri5, KM, 2, AENS_MB_DOPRI5)
+AENS_DEFINE_KERNEL(KN(aens_radau5_d2_), Radau5, KM, 2, AENS_MB_RADAU5)
+AENS_DEFINE_KERNEL(KN(aens_impleuler_d2_), ImplEuler, KM, 2, AENS_MB_EULER)
+AENS_DEFINE_KERNEL(KN(aens_rodas_d2_), Rodas, KM, 2, AENS_MB_RADAU5)
 /* models without events additionally get dense-free variants (no interpolation data kept in registers) */
 AENS_DEFINE_KERNEL(KN(aens_euler_d0_), Euler, KM, kEvents, AENS_MB_EULER)
 AENS_DEFINE_KERNEL(KN(aens_rk34_d0_), RK34, KM, kEvents, AENS_MB_RK34)
@@ -51,15 +58,16 @@ AENS_DEFINE_KERNEL(KN(aens_radau5_d0_), Radau5, KM, kEvents, AENS_MB_RADAU5)
 AENS_DEFINE_KERNEL(KN(aens_impleuler_d0_), ImplEuler, KM, kEvents, AENS_MB_EULER)
 
 extern "C" const void *AENS_CAT(AENS_CAT(aens_kernels_, AENS_KNAME), AENS_SUF)(int solver, int dense) {
+#define AENS_PICK(base) (dense == 2 ? (const void *)KN(base##d2_) : dense ? (const void *)KN(base##d1_) : (const void *)KN(base##d0_))
     switch (solver) {
-    case AENS_SOLVER_EULER: return dense ? (const void *)KN(aens_euler_d1_) : (const void *)KN(aens_euler_d0_);
+    case AENS_SOLVER_EULER: return AENS_PICK(aens_euler_);
     case AENS_SOLVER_RK4: return (const void *)KN(aens_rk4_d0_);
-    case AENS_SOLVER_RK34: return dense ? (const void *)KN(aens_rk34_d1_) : (const void *)KN(aens_rk34_d0_);
-    case AENS_SOLVER_DOPRI5: return dense ? (const void *)KN(aens_dopri5_d1_) : (const void *)KN(aens_dopri5_d0_);
-    case AENS_SOLVER_RADAU5: return dense ? (const void *)KN(aens_radau5_d1_) : (const void *)KN(aens_radau5_d0_);
-    case AENS_SOLVER_IMPLEULER:
-        return dense ? (const void *)KN(aens_impleuler_d1_) : (const void *)KN(aens_impleuler_d0_);
-    case AENS_SOLVER_RODAS: return (const void *)KN(aens_rodas_d1_); /* cont[] is always kept */
+    case AENS_SOLVER_RK34: return AENS_PICK(aens_rk34_);
+    case AENS_SOLVER_DOPRI5: return AENS_PICK(aens_dopri5_);
+    case AENS_SOLVER_RADAU5: return AENS_PICK(aens_radau5_);
+    case AENS_SOLVER_IMPLEULER: return AENS_PICK(aens_impleuler_);
+    case AENS_SOLVER_RODAS: /* cont[] is always kept */
+        return dense == 2 ? (const void *)KN(aens_rodas_d2_) : (const void *)KN(aens_rodas_d1_);
     }
     return nullptr;
 }

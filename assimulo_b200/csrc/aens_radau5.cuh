@@ -295,9 +295,10 @@ AENS_DEV void lu_solc(const double *ar, const double *ai, double *br, double *bi
     }
 }
 
-template <class M, bool DENSE>
+template <class M, int DENSE>
 struct Radau5 {
     static constexpr bool HAS_DENSE = true; /* cont[] is part of the method (Newton start values) */
+    static constexpr bool REDUCE = DENSE == 2;
     static constexpr int N = M::N;
     enum { S_JAC = 0, S_DECOMP = 1, S_STEP = 2 };
     Lane<M> L;
@@ -704,9 +705,10 @@ static __constant__ Consts K = {
 constexpr double uround = 1.e-16; /* rodas_decsol.f:369 */
 }  // namespace ro
 
-template <class M, bool DENSE>
+template <class M, int DENSE>
 struct Rodas {
     static constexpr bool HAS_DENSE = true; /* cont[] is cheap and the event locator needs it */
+    static constexpr bool REDUCE = DENSE == 2;
     static constexpr int N = M::N;
     Lane<M> L;
     double dy1[N], fx[N], cont[4 * N];

@@ -77,6 +77,9 @@ cdef extern from "assimulo_cuda.h":
     int aens_get_summary(aens_handle_t *h, long long *sums, long long *n_not_complete) nogil
     int aens_set_host_mode(aens_handle_t *h, int mode) nogil
     int aens_reduce_final(aens_handle_t *h, double *mean, double *var, double *mn, double *mx, long long *count) nogil
+    int aens_set_row_reduction(aens_handle_t *h, int on) nogil
+    int aens_get_row_reduction(aens_handle_t *h, double *mean, double *var, double *mn, double *mx,
+                               long long *count) nogil
 
 STAT_NAMES = ("nsteps", "nfcns", "nerrfails", "njacs", "nlus", "nstatefcns", "nstateevents", "nstepstotal",
               "ntimeevents", "nniters", "nnfails")
@@ -385,6 +388,25 @@ cdef class Handle:
         cdef int rc
         with nogil:
             rc = aens_reduce_final(self.h, o, o + n, o + 2 * n, o + 3 * n, cp)
+        self._check(rc)
+        return {"mean": out[0], "var": out[1], "min": out[2], "max": out[3], "count": cnt}
+
+    def set_row_reduction(self, on):
+        """Reduce the dense-output rows over the ensemble inside the kernel instead of storing them (call before
+        set_output sets the grid)."""
+        self._check(aens_set_row_reduction(self.h, 1 if on else 0))
+
+    def get_row_reduction(self):
+        """dict(mean, var, min, max [n_out, n], count [n_out]) of the reduced dense-output rows."""
+        cdef int R = self.n_out, n = self.n
+        cdef np.ndarray[double, ndim=3, mode="c"] out = np.empty((4, max(R, 1), n), dtype=np.float64)
+        cdef np.ndarray[np.int64_t, ndim=1, mode="c"] cnt = np.empty(max(R, 1), dtype=np.int64)
+        cdef double *o = &out[0, 0, 0]
+        cdef long long *cp = <long long*>&cnt[0]
+        cdef long long RN = <long long>max(R, 1) * n
+        cdef int rc
+        with nogil:
+            rc = aens_get_row_reduction(self.h, o, o + RN, o + 2 * RN, o + 3 * RN, cp)
         self._check(rc)
         return {"mean": out[0], "var": out[1], "min": out[2], "max": out[3], "count": cnt}
 

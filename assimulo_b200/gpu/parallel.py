@@ -125,3 +125,47 @@ def assemble(t_all, y_all, st_all, stats_all, N_total):
     names = STAT_NAMES
     return {"t": t, "y": y, "status": status, "stats_per_member": {k: stats[i] for i, k in enumerate(names)},
             "statistics": {k: int(stats[i].astype(np.int64).sum()) for i, k in enumerate(names)}}
+
+
+def combine_row_statistics(parts):
+    """Merge per-shard row statistics (dicts with mean/var/min/max [rows, n] and count [rows], as returned by
+    ``solver.row_statistics``) into the statistics of the whole ensemble: counts add, means and variances combine with
+    the pairwise update of Chan, Golub & LeVeque, extrema by min/max.  Rows no member of a shard reached (count 0,
+    NaN entries) do not contribute."""
+    rows, n = np.asarray(parts[0]["mean"]).shape
+    cnt = np.zeros(rows)
+    mean = np.zeros((rows, n))
+    m2 = np.zeros((rows, n))
+    mn = np.full((rows, n), np.inf)
+    mx = np.full((rows, n), -np.inf)
+    for p in parts:
+        cb = np.asarray(p["count"], dtype=np.float64)
+        ok = cb > 0
+        mb = np.where(ok[:, None], np.asarray(p["mean"]), 0.0)
+        m2b = np.where(ok[:, None], np.asarray(p["var"]) * cb[:, None], 0.0)
+        tot = cnt + cb
+        w = np.divide(cb, tot, out=np.zeros_like(tot), where=tot > 0)
+        d = mb - mean
+        mean = mean + d * w[:, None]
+        m2 = m2 + m2b + d * d * (cnt * w)[:, None]
+        cnt = tot
+        mn = np.where(ok[:, None], np.minimum(mn, np.where(ok[:, None], p["min"], np.inf)), mn)
+        mx = np.where(ok[:, None], np.maximum(mx, np.where(ok[:, None], p["max"], -np.inf)), mx)
+    none = (cnt == 0)[:, None]
+    with np.errstate(invalid="ignore", divide="ignore"):
+        var = m2 / cnt[:, None]
+    out = {"mean": np.where(none, np.nan, mean), "var": np.where(none, np.nan, var),
+           "min": np.where(none, np.nan, mn), "max": np.where(none, np.nan, mx), "count": cnt.astype(np.int64)}
+    if "t" in parts[0]:
+        out["t"] = np.asarray(parts[0]["t"])
+    return out
+
+
+def gather_row_statistics(solver, group=None):
+    """Row statistics of a sharded run with ``reduce_rows``: every rank contributes the [rows, n] reductions of its
+    block (a few KB -- the rows themselves never leave the GPUs) and gets the statistics of the whole ensemble."""
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    parts = [None] * world
+    dist.all_gather_object(parts, solver.row_statistics, group=group)
+    return combine_row_statistics(parts)

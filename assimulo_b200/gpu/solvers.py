@@ -65,7 +65,7 @@ class Batched_Explicit_ODE(object):
         self.options = {"report_continuously": False, "display_progress": True, "verbosity": 30, "backward": False,
                         "store_event_points": True, "time_limit": 0, "clock_step": False, "num_threads": 1,
                         "arith": "fast", "refill_threshold": 32, "order": None, "event_slots": 16,
-                        "reuse_buffers": False, "host_chunks": None}
+                        "reuse_buffers": False, "host_chunks": None, "reduce_rows": False}
         self.supports = {"state_events": False, "interpolated_output": False, "report_continuously": False}
         self.problem_info = {"dim": problem.n, "dimRoot": problem.n_g, "state_events": problem.n_g > 0,
                              "jac_fcn": problem.has_jac, "switches": problem.n_sw > 0}
@@ -222,6 +222,11 @@ class Batched_Explicit_ODE(object):
                 h.set_ensemble(self.y, self.problem.p0 if self.problem.n_p else None,
                                self.sw.astype(np.uint8) if self.problem.n_sw else None, self.t)
                 self._dirty = False
+            reduce_rows = bool(self.options["reduce_rows"]) and output_list is not None
+            if reduce_rows != getattr(self, "_reducing", False):
+                h.set_output(None, int(self.options["event_slots"]))  # the mode is switched with no grid set
+                h.set_row_reduction(reduce_rows)
+                self._reducing = reduce_rows
             h.set_output(output_list, int(self.options["event_slots"]))
             h.set_schedule(int(self.options["refill_threshold"]), order)
             h.simulate(tfinal)
@@ -239,7 +244,13 @@ class Batched_Explicit_ODE(object):
             self.sw = sw.astype(bool)
         for k in STAT_NAMES:
             self.statistics[k] = int(sums[k])
-        if output_list is not None:
+        self.row_statistics = None
+        if output_list is not None and self.options["reduce_rows"]:
+            # the rows were reduced over the ensemble on the device: handle_result sees the final states
+            # only, the per-row ensemble statistics are in self.row_statistics
+            self.row_statistics = dict(h.get_row_reduction(), t=np.array(output_list))
+            self.problem.handle_result(self, tfinal, self.y)
+        elif output_list is not None:
             dense = h.get_dense()
             for k, tk in enumerate(output_list):
                 self.problem.handle_result(self, float(tk), dense[k])
@@ -403,6 +414,16 @@ class Batched_Explicit_ODE(object):
     def _set_event_slots(self, v):
         self.options["event_slots"] = int(v)
     event_slots = property(_get_event_slots, _set_event_slots)
+
+    def _get_reduce_rows(self):
+        """True: the rows of the output grid (ncp / ncp_list) are reduced over the ensemble inside the integration
+        kernel -- mean, variance, min, max per state component and the number of members that reached the row, in
+        ``row_statistics`` after simulate() -- instead of being stored per member ([ncp, N, n] through HBM and PCIe)."""
+        return self.options["reduce_rows"]
+
+    def _set_reduce_rows(self, v):
+        self.options["reduce_rows"] = bool(v)
+    reduce_rows = property(_get_reduce_rows, _set_reduce_rows)
 
     # helpers for the option properties below
     def _float_opt(self, key, value, msg):

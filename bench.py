@@ -241,13 +241,14 @@ def run_other_configs(device, peak_tflops, hbm_gbs):
     from assimulo_b200.gpu import _core
     out = []
 
-    def run(name, model, solver, y0, p, sw0, tf, flops, t_grid=None, reverse=False, **opts):
+    def run(name, model, solver, y0, p, sw0, tf, flops, t_grid=None, reverse=False, reduce_rows=False, **opts):
         h = _core.Handle(device)
         h.set_model_builtin(model)
         h.set_ensemble(y0, p, sw0, 0.0)
         d = {"solver": _core.SOLVER_IDS[solver]}
         d.update(opts)
         h.set_opts(d)
+        h.set_row_reduction(reduce_rows)
         h.set_output(t_grid, 16)
         h.set_fetch_reverse(reverse)
         ms = []
@@ -263,7 +264,11 @@ def run_other_configs(device, peak_tflops, hbm_gbs):
                "not_complete": int(nbad), "state_events": int(sums["nstateevents"]),
                "flops_per_accepted_step": flops,
                "fp64_frac": sums["nsteps"] * flops / (ms * 1e-3) / 1e12 / peak_tflops}
-        if t_grid is not None:
+        if reduce_rows:   # the rows never reach HBM: [rows, n] statistics come back instead of [rows, N, n]
+            rs = h.get_row_reduction()
+            rec["rows_reduced_in_kernel"] = int(len(t_grid))
+            rec["members_in_last_row"] = int(rs["count"][-1])
+        elif t_grid is not None:
             nbytes = float(len(t_grid)) * n * 8 * y0.shape[0]
             rec["dense_bytes"] = nbytes
             rec["hbm_write_frac"] = nbytes / (ms * 1e-3) / 1e9 / hbm_gbs
@@ -289,6 +294,9 @@ def run_other_configs(device, peak_tflops, hbm_gbs):
     y0, p = cases.gyro_sweep(1 << 22)
     run("cfg5 Dopri5 gyro (12 states), dense output every 1e-3", "gyro", "Dopri5", y0, p, None, 0.1,
         81 * 12 + 6 * 39 + 20, t_grid=np.linspace(0.0, 0.1, 101)[1:], rtol=1e-8, atol=1e-8)
+    run("cfg5' the same with the 100 rows reduced over the ensemble in the kernel (mean/var/min/max, no dense buffer)",
+        "gyro", "Dopri5", y0, p, None, 0.1, 81 * 12 + 6 * 39 + 20, t_grid=np.linspace(0.0, 0.1, 101)[1:],
+        reduce_rows=True, rtol=1e-8, atol=1e-8)
     return out
 
 

@@ -200,6 +200,16 @@ int aens_get_stats_sum(aens_handle_t *h, long long *sums /*[AENS_NSTATS]*/);
  * component, over the members whose status is AENS_ST_COMPLETE: mean[n], var[n] (population variance), min[n],
  * max[n], count[n].  Any pointer may be NULL. */
 int aens_reduce_final(aens_handle_t *h, double *mean, double *var, double *min, double *max, long long *count);
+/* Row reduction mode -- the ensemble-level counterpart of handle_result() being called with every dense-output row
+ * (src/explicit_ode.pyx:308-318, src/problem.pyx:145-158): with on != 0 the rows of the output grid are not stored
+ * per member ([n_out][n][N] in HBM, N x n_out x n doubles to download) but reduced over the ensemble inside the
+ * integration kernel.  Call before aens_set_output; aens_get_dense then fails.  After aens_simulate,
+ * aens_get_row_reduction returns, per grid row and state component, over the members that reached that row:
+ * mean[n_out][n], var[n_out][n] (population variance), min[n_out][n], max[n_out][n] and count[n_out]
+ * (any pointer may be NULL; rows no member reached hold NaN and count 0).  Sums are accumulated in the order the
+ * warps finish rows, so mean and var are reproducible to rounding only; min, max and count are exact. */
+int aens_set_row_reduction(aens_handle_t *h, int on);
+int aens_get_row_reduction(aens_handle_t *h, double *mean, double *var, double *min, double *max, long long *count);
 /* dense output row `slot` (0..n_out-1) as y_out[N][n]; rows beyond a member's end time are NaN */
 int aens_get_dense(aens_handle_t *h, int slot, double *y_out);
 /* whole buffer, y_out[n_out][N][n] */

@@ -512,3 +512,91 @@ def test_continuation_restarts_like_the_reference(name, opts):
     o2 = O.simulate("vdp", name, o1["y"], mu, t0=1.0, tf=2.0, **{k: (int(v) if k == "usejac" else v) for k, v in opts.items()})
     assert sim.t == 2.0 and rel_err(sim.y, o2["y"]) <= 1e-9
     assert sim.statistics["nsteps"] == int(o2["stats"]["nsteps"].sum())        # statistics restart with every simulate()
+
+
+def _row_reduction_case(cls, prob_kw, tf, ncp, N_expect=None, **opts):
+    """simulate the same ensemble twice -- rows stored per member, rows reduced in the kernel -- and compare the
+    device's row statistics with numpy reductions of the stored rows"""
+    from assimulo_b200.gpu import Batched_Explicit_Problem
+    sims = []
+    for red in (False, True):
+        sim = cls(Batched_Explicit_Problem(**prob_kw))
+        for k, v in opts.items():
+            setattr(sim, k, v)
+        sim.reduce_rows = red
+        t, y = sim.simulate(tf, ncp)
+        sims.append((sim, t, y))
+    (a, ta, ya), (b, tb, yb) = sims
+    rows = np.asarray(ya)[1:]                                    # [ncp, N, n], NaN where a member never got there
+    rs = b.row_statistics
+    assert a.row_statistics is None and rs is not None
+    assert np.allclose(rs["t"], ta[1:]) and tb == [ta[0], ta[-1]] and np.asarray(yb).shape[0] == 2
+    assert rel_err(b.y, a.y) <= 1e-12 and np.array_equal(b.status, a.status)   # the integration itself is untouched
+    for k in ("nsteps", "nfcns", "nstateevents"):
+        assert a.statistics[k] == b.statistics[k]
+    reached = ~np.isnan(rows[:, :, 0])
+    assert np.array_equal(rs["count"], reached.sum(axis=1))
+    for r in range(rows.shape[0]):
+        v = rows[r][reached[r]]
+        if len(v) == 0:
+            assert np.isnan(rs["mean"][r]).all() and np.isnan(rs["min"][r]).all()
+            continue
+        scale = np.abs(v).max(axis=0) + 1e-300
+        if opts.get("arith") == "strict":   # no FMA contraction: both kernels evaluate the interpolant identically
+            assert np.array_equal(rs["min"][r], v.min(axis=0)) and np.array_equal(rs["max"][r], v.max(axis=0))
+        else:                               # separately compiled kernels may contract the interpolant differently
+            assert (np.abs(rs["min"][r] - v.min(axis=0)) <= 1e-14 * scale).all()
+            assert (np.abs(rs["max"][r] - v.max(axis=0)) <= 1e-14 * scale).all()
+        assert (np.abs(rs["mean"][r] - v.mean(axis=0)) <= 1e-13 * scale).all()          # summation order only
+        assert (np.abs(rs["var"][r] - v.var(axis=0)) <= 1e-11 * scale ** 2).all()
+    return a, b
+
+
+def test_row_reduction_dopri5_vdp_ragged_ensemble():
+    """ensemble mean/var/min/max of every dense-output row, reduced inside the integration kernel."""
+    from assimulo_b200.gpu import Dopri5
+    for N in (1, 31, 5000):
+        y0, mu = cases.vdp_sweep(max(N, 2))
+        _row_reduction_case(Dopri5, dict(model="vdp", y0=y0[:N], p0=mu[:N]), 2.0, 50, rtol=1e-6, atol=1e-6)
+    _row_reduction_case(Dopri5, dict(model="vdp", y0=y0, p0=mu), 2.0, 50, rtol=1e-6, atol=1e-6, arith="strict")
+
+
+@pytest.mark.parametrize("name", ["ExplicitEuler", "RungeKutta34", "Dopri5", "Radau5ODE", "RodasODE"])
+def test_row_reduction_with_state_events_every_solver(name):
+    """bouncing ball: lanes of one warp reach the rows in different steps and from both emission sites (event branch and
+    plain step), which is what the per-warp lock of aens_reduce_grid is for"""
+    import assimulo_b200.gpu as G
+    y0, p, sw0 = cases.ball_sweep(3001)
+    opts = dict(h=1e-3) if name == "ExplicitEuler" else dict(rtol=1e-6, atol=1e-6)
+    a, b = _row_reduction_case(getattr(G, name), dict(model="ball", y0=y0, p0=p, sw0=sw0), 3.0, 64, **opts)
+    assert a.statistics["nstateevents"] > 3001
+
+
+def test_row_reduction_gyro_twelve_states_and_failed_members():
+    from assimulo_b200.gpu import Dopri5
+    y0, p = cases.gyro_sweep(4099)
+    _row_reduction_case(Dopri5, dict(model="gyro", y0=y0, p0=p), 0.1, 100, rtol=1e-8, atol=1e-8)
+    _row_reduction_case(Dopri5, dict(model="gyro", y0=y0[:999], p0=p[:999]), 0.1, 100, rtol=1e-8, atol=1e-8, arith="strict")
+    # members that stop early (maxsteps) contribute to the rows they reached only
+    y0, mu = cases.vdp_sweep(5000)
+    a, b = _row_reduction_case(Dopri5, dict(model="vdp", y0=y0, p0=mu), 2.0, 40, maxsteps=60)
+    assert 0 < b.n_not_complete < 5000
+    c = b.row_statistics["count"]
+    assert c[0] == 5000 and c[-1] == 5000 - b.n_not_complete and (np.diff(c) <= 0).all()
+
+
+def test_row_reduction_nvrtc_model_and_mode_switching():
+    from assimulo_b200.gpu import Batched_Explicit_Problem, Dopri5
+    y0, mu = cases.vdp_sweep(777)
+    prob = dict(source=VDP_SRC, n=2, n_p=1, has_jac=True, y0=y0, p0=mu)
+    _row_reduction_case(Dopri5, prob, 2.0, 25, rtol=1e-6, atol=1e-6)
+    # one solver object: stored rows, then reduced rows, then stored rows again
+    sim = Dopri5(Batched_Explicit_Problem(model="vdp", y0=y0, p0=mu))
+    t, y = sim.simulate(1.0, 10)
+    assert np.asarray(y).shape == (11, 777, 2) and sim.row_statistics is None
+    sim.reduce_rows = True
+    sim.simulate(2.0, 10)
+    assert sim.row_statistics["mean"].shape == (10, 2) and (sim.row_statistics["count"] == 777).all()
+    sim.reduce_rows = False
+    t, y = sim.simulate(3.0, 10)
+    assert np.asarray(y).shape == (11, 777, 2) and sim.row_statistics is None

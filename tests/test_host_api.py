@@ -145,3 +145,30 @@ def test_general_solver_options_of_the_reference():
     with pytest.raises(AssimuloException):
         sim.backward = True
     assert sim.backward is False
+
+
+def test_combine_row_statistics_equals_statistics_of_the_union():
+    """parallel.combine_row_statistics: shard-wise (count, mean, var, min, max) -> whole-ensemble statistics, with
+    rows a shard never reached (count 0 / NaN) and a one-member shard."""
+    from assimulo_b200.gpu import parallel
+    rng = np.random.default_rng(0)
+    N, R, n = 1000, 7, 3
+    x = rng.normal(5.0, 2.0, (R, N, n))
+    reach = rng.random((R, N)) < 0.8
+    reach[3, :400] = False
+    reach[5, :] = False
+
+    def stats(lo, hi):
+        out = {k: np.full((R, n), np.nan) for k in ("mean", "var", "min", "max")}
+        out["count"] = np.zeros(R, dtype=np.int64)
+        for r in range(R):
+            v = x[r, lo:hi][reach[r, lo:hi]]
+            out["count"][r] = len(v)
+            if len(v):
+                out["mean"][r], out["var"][r], out["min"][r], out["max"][r] = v.mean(0), v.var(0), v.min(0), v.max(0)
+        return out
+    full, c = stats(0, N), parallel.combine_row_statistics([stats(0, 400), stats(400, 401), stats(401, N)])
+    assert np.array_equal(c["count"], full["count"]) and c["count"][5] == 0 and np.isnan(c["mean"][5]).all()
+    ok = full["count"] > 0
+    assert np.array_equal(c["min"][ok], full["min"][ok]) and np.array_equal(c["max"][ok], full["max"][ok])
+    assert np.allclose(c["mean"][ok], full["mean"][ok], rtol=1e-13) and np.allclose(c["var"][ok], full["var"][ok], rtol=1e-12)

@@ -39,6 +39,23 @@ class _OracleBackedSolver(object):
         self.statistics = _S()
 
 
+GRID = np.linspace(0.0, 2.0, 9)[1:]
+
+
+def _oracle_rows(y0, mu):
+    """dense-output rows [rows, members, n] of a block, from the oracle"""
+    import ens_oracle as O
+    return np.transpose(O.simulate("vdp", "Dopri5", y0, mu, tf=2.0, t_grid=GRID, rtol=1e-6, atol=1e-6)["dense"], (1, 0, 2))
+
+
+class _RowStats(object):
+    """what a solver with reduce_rows = True holds after simulate(): the statistics of its own block"""
+
+    def __init__(self, rows):
+        self.row_statistics = {"mean": rows.mean(axis=1), "var": rows.var(axis=1), "min": rows.min(axis=1),
+                               "max": rows.max(axis=1), "count": np.full(rows.shape[0], rows.shape[1]), "t": GRID}
+
+
 def _worker(rank, port, q):
     for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests", "golden")):
         sys.path.insert(0, p)
@@ -58,8 +75,10 @@ def _worker(rank, port, q):
     y0b, pb, swb = cases.ball_sweep(N)
     ball = parallel.shard_problem(Batched_Explicit_Problem(model="ball", y0=y0b, p0=pb, sw0=swb), rank, WORLD)
     gb = parallel.gather_final(_OracleBackedSolver(ball), N)
+    # row reduction mode: each rank contributes the [rows, n] statistics of its block, never the rows
+    rs = parallel.gather_row_statistics(_RowStats(_oracle_rows(y0[lo:hi], mu[lo:hi])))
     q.put((rank, g["y"], g["t"], g["status"], g["statistics"]["nsteps"], g["stats_per_member"]["nsteps"],
-           gb["y"], gb["event_count"], gb["event_t"], gb["event_info"]))
+           gb["y"], gb["event_count"], gb["event_t"], gb["event_info"], rs))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -82,7 +101,12 @@ def test_two_rank_gloo_gather_matches_single_process():
     ref = O.simulate("vdp", "Dopri5", y0, mu, tf=2.0, rtol=1e-6, atol=1e-6)
     y0b, pb, swb = cases.ball_sweep(N)
     refb = O.simulate("ball", "Dopri5", y0b, pb, swb, tf=3.0, max_ev=SLOTS, rtol=1e-6, atol=1e-6)
-    for rank, y, t, st, nsteps, per, yb, evc, evt, evi in res:
+    rows = _oracle_rows(y0, mu)
+    for rank, y, t, st, nsteps, per, yb, evc, evt, evi, rs in res:
+        assert (rs["count"] == N).all() and np.array_equal(rs["t"], GRID)
+        assert np.array_equal(rs["min"], rows.min(axis=1)) and np.array_equal(rs["max"], rows.max(axis=1))
+        assert np.allclose(rs["mean"], rows.mean(axis=1), rtol=1e-13, atol=1e-14)
+        assert np.allclose(rs["var"], rows.var(axis=1), rtol=1e-11, atol=1e-14)
         assert np.array_equal(yb, refb["y"]) and np.array_equal(evc, refb["stats"]["nstateevents"])
         m = np.isfinite(refb["ev_t"])
         assert np.array_equal(evt[m], refb["ev_t"][m]) and np.array_equal(evi[m], refb["ev_info"][m])

@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Run ONE BASELINE config a few times (for ncu captures):  python tools/run_cfg.py {rk4|rk34|dopri5|ball|radau|rodas|gyro|gyrodense} [reps]"""
+"""Run ONE BASELINE config a few times (for ncu captures):  python tools/run_cfg.py {rk4|rk34|dopri5|ball|radau|rodas|gyro|gyrodense|gyrored} [reps]"""
 import os, sys
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -27,7 +27,7 @@ elif which == "radau":
 else:
     y0, p = cases.gyro_sweep(1 << 22); sw0 = None; model = "gyro"; tf = 0.1
     solver, opts = "Dopri5", dict(rtol=1e-8, atol=1e-8)
-    if which == "gyrodense":
+    if which in ("gyrodense", "gyrored"):
         grid = np.linspace(0, 0.1, 101)[1:]
 h = _core.Handle(0)
 h.set_model_builtin(model)
@@ -35,8 +35,14 @@ h.set_ensemble(y0, p, sw0, 0.0)
 d = {"solver": _core.SOLVER_IDS[solver]}
 d.update(opts)
 h.set_opts(d)
+if which == "gyrored":
+    h.set_row_reduction(True)
 h.set_output(grid, 16)
 h.set_fetch_reverse(rev)
 for _ in range(reps):
     h.reset(); h.simulate(tf)
     print(which, "kernel ms", h.last_kernel_ms(), h.get_summary())
+if which == "gyrored":
+    import time
+    t0 = time.perf_counter(); rs = h.get_row_reduction(); t1 = time.perf_counter()
+    print("get_row_reduction %.2f ms; count[-1] %d; mean[-1][:3] %s" % (1e3 * (t1 - t0), rs["count"][-1], rs["mean"][-1][:3]))
