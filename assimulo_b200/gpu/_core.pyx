@@ -77,6 +77,8 @@ cdef extern from "assimulo_cuda.h":
     int aens_get_summary(aens_handle_t *h, long long *sums, long long *n_not_complete) nogil
     int aens_set_host_mode(aens_handle_t *h, int mode) nogil
     int aens_reduce_final(aens_handle_t *h, double *mean, double *var, double *mn, double *mx, long long *count) nogil
+    int aens_reduce_end_times(aens_handle_t *h, int status, double *mean, double *var, double *mn, double *mx,
+                              long long *count) nogil
     int aens_set_row_reduction(aens_handle_t *h, int on) nogil
     int aens_get_row_reduction(aens_handle_t *h, double *mean, double *var, double *mn, double *mx,
                                long long *count) nogil
@@ -390,6 +392,17 @@ cdef class Handle:
             rc = aens_reduce_final(self.h, o, o + n, o + 2 * n, o + 3 * n, cp)
         self._check(rc)
         return {"mean": out[0], "var": out[1], "min": out[2], "max": out[3], "count": cnt}
+
+    def reduce_end_times(self, int status=1):
+        """mean / var / min / max / count of the end times of the members with the given status, reduced on the
+        device (status 1 = terminated by handle_event: first-passage times)."""
+        cdef double o[4]
+        cdef long long cnt = 0
+        cdef int rc
+        with nogil:
+            rc = aens_reduce_end_times(self.h, status, &o[0], &o[1], &o[2], &o[3], &cnt)
+        self._check(rc)
+        return {"mean": o[0], "var": o[1], "min": o[2], "max": o[3], "count": cnt}
 
     def set_row_reduction(self, on):
         """Reduce the dense-output rows over the ensemble inside the kernel instead of storing them (call before

@@ -271,6 +271,14 @@ class Batched_Explicit_ODE(object):
             raise AssimuloException("simulate() first.")
         return self._handle.reduce_final()
 
+    def end_time_statistics(self, status=1):
+        """mean / var / min / max / count of the members' end times over the members with the given status code,
+        reduced on the device.  status=1 (terminated by handle_event) gives first-passage-time statistics of a model
+        that stops at its first event."""
+        if self._handle is None or not self._launched:
+            raise AssimuloException("simulate() first.")
+        return self._handle.reduce_end_times(int(status))
+
     @property
     def status(self):
         """Per-member status codes (include/assimulo_cuda.h AENS_ST_*); 0 = reached tfinal."""

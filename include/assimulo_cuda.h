@@ -200,6 +200,12 @@ int aens_get_stats_sum(aens_handle_t *h, long long *sums /*[AENS_NSTATS]*/);
  * component, over the members whose status is AENS_ST_COMPLETE: mean[n], var[n] (population variance), min[n],
  * max[n], count[n].  Any pointer may be NULL. */
 int aens_reduce_final(aens_handle_t *h, double *mean, double *var, double *min, double *max, long long *count);
+/* The same reduction over the members' END TIMES, restricted to the members whose status equals `status`
+ * (scalars: mean, var, min, max, count).  With status = AENS_ST_TERMINATED these are first-passage-time statistics:
+ * a model whose handle_event returns "terminate" (the reference's TerminateSimulation, src/explicit_ode.pyx:259-262)
+ * stops each member at its first event, and the end time of a terminated member is the located event time. */
+int aens_reduce_end_times(aens_handle_t *h, int status, double *mean, double *var, double *min, double *max,
+                          long long *count);
 /* Row reduction mode -- the ensemble-level counterpart of handle_result() being called with every dense-output row
  * (src/explicit_ode.pyx:308-318, src/problem.pyx:145-158): with on != 0 the rows of the output grid are not stored
  * per member ([n_out][n][N] in HBM, N x n_out x n doubles to download) but reduced over the ensemble inside the

@@ -600,3 +600,25 @@ def test_row_reduction_nvrtc_model_and_mode_switching():
     sim.reduce_rows = False
     t, y = sim.simulate(3.0, 10)
     assert np.asarray(y).shape == (11, 777, 2) and sim.row_statistics is None
+
+
+def test_first_passage_time_statistics_on_device():
+    """aens_reduce_end_times: members stopped by handle_event at their first event (TerminateSimulation) -- the
+    statistics of their end times are first-passage-time statistics; y' = 1, event at y = p => passage time p."""
+    from assimulo_b200.gpu import Batched_Explicit_Problem, Dopri5
+    N = 3000
+    p = np.linspace(0.1, 2.9, N)[:, None]
+    p[::7] = 5.0                                   # these never get there before tfinal = 3
+    sim = Dopri5(Batched_Explicit_Problem(source=TERMINATE_SRC, n=1, n_p=1, n_g=1, n_sw=1, y0=np.zeros((N, 1)), p0=p,
+                                          sw0=np.ones((N, 1), dtype=bool)))
+    sim.simulate(3.0)
+    hit = p[:, 0] < 3.0
+    assert np.array_equal(sim.status == 1, hit)
+    fp = sim.end_time_statistics(status=1)
+    assert fp["count"] == hit.sum()
+    assert abs(fp["mean"] - p[hit, 0].mean()) <= 1e-9 and abs(fp["var"] - p[hit, 0].var()) <= 1e-9
+    assert abs(fp["min"] - p[hit, 0].min()) <= 1e-9 and abs(fp["max"] - p[hit, 0].max()) <= 1e-9
+    done = sim.end_time_statistics(status=0)
+    assert done["count"] == N - hit.sum() and done["min"] == done["max"] == 3.0
+    none = sim.end_time_statistics(status=-2)
+    assert none["count"] == 0 and np.isnan(none["mean"])
