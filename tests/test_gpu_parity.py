@@ -489,3 +489,38 @@ def test_rodas_solver_class():
     assert len(t) == 5 and rel_err(y[-1], o["y"]) <= 1e-5
     assert abs(sim.statistics["nsteps"] - int(o["stats"]["nsteps"].sum())) <= 0.02 * o["stats"]["nsteps"].sum()
     assert sim.statistics["nlus"] > 0 and sim.statistics["njacs"] > 0
+
+
+def test_known_answers_of_the_reference_examples_on_the_device():
+    """The pins SURVEY 8(c) lists for the benchmark MODELS, evaluated by the device path itself (both arithmetic builds):
+    Robertson y1(0.4) (examples/radau5ode_with_jac_sparse.py:91) and y(4) (examples/cvode_with_parameters.py:89-91),
+    gyro y(0.1) (examples/cvode_gyro.py:85-86), bouncing ball first impact sqrt(2*2/9.81) and the impact sequence of
+    examples/lsodar_bouncing_ball.py."""
+    from assimulo_b200.gpu import Batched_Explicit_Problem, Dopri5, Radau5ODE, RodasODE, RungeKutta34
+    for arith in ("strict", "fast"):
+        rob = dict(model="robertson", y0=[[1.0, 0.0, 0.0]], p0=[[0.04, 1e4, 3e7]])
+        sim = Radau5ODE(Batched_Explicit_Problem(**rob))
+        sim.arith, sim.rtol, sim.atol = arith, 1e-4, cases.ROBERTSON_ATOL
+        sim.simulate(0.4)
+        assert abs(sim.y[0, 0] - 0.9851) < 1e-3
+        for cls in (Radau5ODE, RodasODE):
+            sim = cls(Batched_Explicit_Problem(**rob))
+            sim.arith, sim.rtol, sim.atol = arith, 1e-8, [1e-10, 1e-14, 1e-10]
+            sim.simulate(4.0)
+            assert np.abs(sim.y[0] - [0.905518032, 2.24046805e-5, 0.0944595637]).max() < 1e-4
+        gy = Dopri5(Batched_Explicit_Problem(model="gyro", y0=[np.hstack([[1e4, 5e4, 6e4], np.eye(3).reshape(9)])],
+                                             p0=[[1000.0, 5000.0, 6000.0]]))
+        gy.arith, gy.rtol, gy.atol = arith, 1e-10, 1e-10
+        gy.simulate(0.1)
+        # the example's y[0] comes from CVode BDF(maxord 2) and carries a 2.3e-4 error (see test_oracle_golden.py)
+        assert abs(gy.y[0, 0] - 692.800241862) < 1e-3 and abs(gy.y[0, 0] - 692.8004700450) < 1e-7
+        assert abs(gy.y[0, 8] - 7.08468221e-1) < 1e-6
+        for cls in (Dopri5, RungeKutta34):
+            ball = cls(Batched_Explicit_Problem(model="ball", y0=[[2.0, 0.0]], p0=[[-9.81, 0.88]], sw0=[[1, 0]]))
+            ball.arith = arith
+            ball.simulate(3.0)
+            te = ball.event_times(0)
+            # impacts (every second event: the apex events lie between them), SURVEY 8(c) probe confirmations
+            want = [0.638550856814101, 1.200475610810578, 1.762400364807010, 2.256894148324066, 2.751387931840934]
+            hits = [t for t in te if any(abs(t - w) < 1e-6 for w in want)]
+            assert len(hits) == 5 and abs(hits[0] - np.sqrt(2 * 2 / 9.81)) < 1e-9
