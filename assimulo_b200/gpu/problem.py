@@ -70,6 +70,10 @@ class Batched_Explicit_Problem(object):
         if N is not None:
             sizes.append(int(N))
         N = max(sizes) if sizes else 1
+        if N < 1:
+            raise AssimuloException("The ensemble is empty: y0 / p0 / sw0 need at least one member.")
+        if y0.shape[-1] != self.n or y0.ndim > 2:
+            raise AssimuloException("y0 must have shape [n] or [N, n] with n = %d." % self.n)
         self.N = N
         self.y0 = np.ascontiguousarray(np.broadcast_to(y0.reshape(-1, self.n) if y0.ndim == 2 else y0[None, :],
                                                        (N, self.n)))

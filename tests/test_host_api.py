@@ -172,3 +172,11 @@ def test_combine_row_statistics_equals_statistics_of_the_union():
     ok = full["count"] > 0
     assert np.array_equal(c["min"][ok], full["min"][ok]) and np.array_equal(c["max"][ok], full["max"][ok])
     assert np.allclose(c["mean"][ok], full["mean"][ok], rtol=1e-13) and np.allclose(c["var"][ok], full["var"][ok], rtol=1e-12)
+
+
+def test_empty_and_misshapen_ensembles_are_rejected_up_front():
+    with pytest.raises(AssimuloException, match="empty"):
+        Batched_Explicit_Problem(model="vdp", y0=np.zeros((0, 2)), p0=np.zeros((0, 1)))
+    with pytest.raises(AssimuloException, match="shape"):
+        Batched_Explicit_Problem(model="vdp", y0=np.zeros((5, 3)))
+    assert Batched_Explicit_Problem(model="vdp", y0=[2.0, -0.6], N=7).y0.shape == (7, 2)
