@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Run ONE BASELINE config a few times (for ncu captures):  python tools/run_cfg.py {rk4|rk34|dopri5|ball|radau|rodas|gyro|gyrodense|gyrored} [reps]"""
+"""Run ONE BASELINE config a few times (for ncu captures):  python tools/run_cfg.py {rk4|rk34|dopri5|dopri5_23|ball|radau|rodas|gyro|gyrodense|gyrored} [reps]"""
 import os, sys
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -12,10 +12,13 @@ reps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 N = 1 << 20
 grid = None
 rev = False
-if which in ("rk4", "rk34", "dopri5"):
+if which in ("rk4", "rk34", "dopri5", "dopri5_23"):
+    if which == "dopri5_23":
+        N = 1 << 23  # the bench headline size
     y0, p = cases.vdp_sweep(N); sw0 = None; model = "vdp"; tf = 2.0; rev = True
     solver, opts = {"rk4": ("RungeKutta4", dict(h=1e-3)), "rk34": ("RungeKutta34", dict(rtol=1e-6, atol=1e-6, inith=0.01)),
-                    "dopri5": ("Dopri5", dict(rtol=1e-6, atol=1e-6))}[which]
+                    "dopri5": ("Dopri5", dict(rtol=1e-6, atol=1e-6)),
+                    "dopri5_23": ("Dopri5", dict(rtol=1e-6, atol=1e-6))}[which]
 elif which == "ball":
     y0, p, sw0 = cases.ball_sweep(N); model = "ball"; tf = 3.0; solver, opts = "Dopri5", dict(rtol=1e-6, atol=1e-6)
 elif which == "rodas":
