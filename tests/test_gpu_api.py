@@ -559,6 +559,12 @@ def test_row_reduction_dopri5_vdp_ragged_ensemble():
         y0, mu = cases.vdp_sweep(max(N, 2))
         _row_reduction_case(Dopri5, dict(model="vdp", y0=y0[:N], p0=mu[:N]), 2.0, 50, rtol=1e-6, atol=1e-6)
     _row_reduction_case(Dopri5, dict(model="vdp", y0=y0, p0=mu), 2.0, 50, rtol=1e-6, atol=1e-6, arith="strict")
+    # lanes refilled one by one / in small groups: the warp's lanes are at unrelated rows all the time
+    for thr in (1, 8):
+        _row_reduction_case(Dopri5, dict(model="vdp", y0=y0, p0=mu), 2.0, 50, rtol=1e-6, atol=1e-6, refill_threshold=thr,
+                            order="two-ended")
+    rng = np.random.default_rng(5)
+    _row_reduction_case(Dopri5, dict(model="vdp", y0=y0, p0=mu), 2.0, 7, rtol=1e-6, atol=1e-6, order=rng.permutation(5000))
 
 
 @pytest.mark.parametrize("name", ["ExplicitEuler", "RungeKutta34", "Dopri5", "Radau5ODE", "RodasODE"])
