@@ -146,6 +146,17 @@ struct Lane {
     }
 
     AENS_DEV void rhs(double tt, const double *yy, double *yd) { M::rhs(tt, yy, sw, p, yd); }
+    /* hk = h * f(tt, yy): the model's fused form where it has one (FAST build only: it re-associates a product) */
+    AENS_DEV void rhs_h(double h, double tt, const double *yy, double *hk) {
+        if constexpr (M::HAS_RHS_H && !AENS_STRICT) {
+            M::rhs_h(h, tt, yy, sw, p, hk);
+        } else {
+            double yd[M::N];
+            M::rhs(tt, yy, sw, p, yd);
+#pragma unroll
+            for (int i = 0; i < M::N; ++i) hk[i] = h * yd[i];
+        }
+    }
 
     AENS_DEV void load(const aens_args_t &a, long long idx) {
         if (a.in_y) { /* zero-copy fetch from the caller's member-major host arrays */
@@ -1148,19 +1159,17 @@ struct Dopri5 {
                 E[i] = T.e1 * hk1[i];
                 if (DENSE) D[i] = T.d1 * hk1[i];
             }
-            L.rhs(fma(T.c2, h, x), kk, k2);
+            L.rhs_h(h, fma(T.c2, h, x), kk, hk);
 #pragma unroll
             for (int i = 0; i < N; ++i) {
-                hk[i] = h * k2[i];
                 A3[i] = fma(T.a32, hk[i], A3[i]);
                 A4[i] = fma(T.a42, hk[i], A4[i]);
                 A5[i] = fma(T.a52, hk[i], A5[i]);
                 A6[i] = fma(T.a62, hk[i], A6[i]);
             }
-            L.rhs(fma(T.c3, h, x), A3, kk);
+            L.rhs_h(h, fma(T.c3, h, x), A3, hk);
 #pragma unroll
             for (int i = 0; i < N; ++i) {
-                hk[i] = h * kk[i];
                 A4[i] = fma(T.a43, hk[i], A4[i]);
                 A5[i] = fma(T.a53, hk[i], A5[i]);
                 A6[i] = fma(T.a63, hk[i], A6[i]);
@@ -1168,29 +1177,26 @@ struct Dopri5 {
                 E[i] = fma(T.e3, hk[i], E[i]);
                 if (DENSE) D[i] = fma(T.d3, hk[i], D[i]);
             }
-            L.rhs(fma(T.c4, h, x), A4, kk);
+            L.rhs_h(h, fma(T.c4, h, x), A4, hk);
 #pragma unroll
             for (int i = 0; i < N; ++i) {
-                hk[i] = h * kk[i];
                 A5[i] = fma(T.a54, hk[i], A5[i]);
                 A6[i] = fma(T.a64, hk[i], A6[i]);
                 y1[i] = fma(T.a74, hk[i], y1[i]);
                 E[i] = fma(T.e4, hk[i], E[i]);
                 if (DENSE) D[i] = fma(T.d4, hk[i], D[i]);
             }
-            L.rhs(fma(T.c5, h, x), A5, kk);
+            L.rhs_h(h, fma(T.c5, h, x), A5, hk);
 #pragma unroll
             for (int i = 0; i < N; ++i) {
-                hk[i] = h * kk[i];
                 A6[i] = fma(T.a65, hk[i], A6[i]);
                 y1[i] = fma(T.a75, hk[i], y1[i]);
                 E[i] = fma(T.e5, hk[i], E[i]);
                 if (DENSE) D[i] = fma(T.d5, hk[i], D[i]);
             }
-            L.rhs(xph, A6, kk);
+            L.rhs_h(h, xph, A6, hk);
 #pragma unroll
             for (int i = 0; i < N; ++i) {
-                hk[i] = h * kk[i];
                 y1[i] = fma(T.a76, hk[i], y1[i]);
                 E[i] = fma(T.e6, hk[i], E[i]);
                 if (DENSE) D[i] = fma(T.d6, hk[i], D[i]);

@@ -31,6 +31,10 @@
 /* what a model inherits unless it says otherwise: no parameter preparation, no time events */
 struct AensModelDefaults {
     static constexpr bool HAS_TE = false;
+    /* optional fused "step times right-hand side": rhs_h(h, t, y, sw, p, hk) returns hk = h * f(t, y).  The explicit
+     * Runge-Kutta stages of the FAST Dopri5 build only ever need h * k_j; a model whose f is a product with a
+     * parameter can fold h into that factor once per step (Van der Pol: (h mu) * w instead of h * (mu * w)). */
+    static constexpr bool HAS_RHS_H = false;
     static AENS_DEV void prep(double *) {}
     static AENS_DEV double time_events(double, const double *, const unsigned char *, const double *) {
         return AENS_NO_TIME_EVENT;
@@ -44,6 +48,12 @@ struct AensVdp : AensModelDefaults {
     static AENS_DEV void rhs(double, const double *y, const unsigned char *, const double *p, double *yd) {
         yd[0] = y[1];
         yd[1] = p[0] * ((1. - y[0] * y[0]) * y[1] - y[0]);
+    }
+    static constexpr bool HAS_RHS_H = true;
+    static AENS_DEV void rhs_h(double h, double, const double *y, const unsigned char *, const double *p, double *hk) {
+        const double hmu = h * p[0]; /* common to the stages of one attempt */
+        hk[0] = h * y[1];
+        hk[1] = hmu * ((1. - y[0] * y[0]) * y[1] - y[0]);
     }
     static AENS_DEV void jac(double, const double *y, const unsigned char *, const double *p, double *J) {
         J[0] = 0.;
@@ -225,6 +235,12 @@ struct AensUser : AensModelDefaults {
 #endif
     static constexpr int N = AENS_USER_N, NP = AENS_USER_NP, NG = AENS_USER_NG, NSW = AENS_USER_NSW;
     static constexpr bool HAS_JAC = (AENS_USER_HAS_JAC != 0);
+#if defined(AENS_USER_HAS_RHS_H) && AENS_USER_HAS_RHS_H
+    static constexpr bool HAS_RHS_H = true;
+    static AENS_DEV void rhs_h(double h, double t, const double *y, const unsigned char *sw, const double *p, double *hk) {
+        aens_rhs_h(h, t, y, sw, p, hk);
+    }
+#endif
     static AENS_DEV void rhs(double t, const double *y, const unsigned char *sw, const double *p, double *yd) {
         aens_rhs(t, y, sw, p, yd);
     }

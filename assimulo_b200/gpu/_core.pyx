@@ -85,7 +85,7 @@ cdef extern from "assimulo_cuda.h":
 
 STAT_NAMES = ("nsteps", "nfcns", "nerrfails", "njacs", "nlus", "nstatefcns", "nstateevents", "nstepstotal",
               "ntimeevents", "nniters", "nnfails")
-MODEL_HAS_JAC, MODEL_TIME_EVENTS = 1, 2
+MODEL_HAS_JAC, MODEL_TIME_EVENTS, MODEL_RHS_H = 1, 2, 4
 SOLVER_IDS = {"ExplicitEuler": 0, "RungeKutta4": 1, "RungeKutta34": 2, "Dopri5": 3, "Radau5ODE": 4,
               "ImplicitEuler": 5, "RodasODE": 6}
 MAX_N = 16

@@ -43,7 +43,7 @@ class Batched_Explicit_Problem(object):
     """
 
     def __init__(self, model=None, y0=None, p0=None, sw0=None, t0=0.0, name="---", source=None, n=None, n_p=0,
-                 n_g=0, n_sw=0, has_jac=False, N=None, time_events=False):
+                 n_g=0, n_sw=0, has_jac=False, N=None, time_events=False, fused_rhs=False):
         if (model is None) == (source is None):
             raise AssimuloException("Give exactly one of model= (built-in) or source= (CUDA C string).")
         if model is not None:
@@ -59,6 +59,8 @@ class Batched_Explicit_Problem(object):
         self.n, self.n_p, self.n_g, self.n_sw, self.has_jac = int(n), int(n_p), int(n_g), int(n_sw), bool(has_jac)
         #: the model defines aens_time_events / aens_handle_time_event (Explicit_Problem.time_events)
         self.time_events = bool(time_events)
+        #: the source also defines aens_rhs_h (hk = h * f, AENS_MODEL_RHS_H); built-in models carry their own
+        self.fused_rhs = bool(fused_rhs) and source is not None
         self.t0 = float(t0)
         if y0 is None:
             raise AssimuloException("y0 must be given.")

@@ -101,7 +101,7 @@ class Batched_Explicit_ODE(object):
             else:
                 p = self.problem
                 self._handle.set_model_source(p.source, p.n, p.n_p, p.n_g, p.n_sw,
-                                              int(bool(p.has_jac)) | (2 if p.time_events else 0))
+                                              int(bool(p.has_jac)) | (2 if p.time_events else 0) | (4 if p.fused_rhs else 0))
         return self._handle
 
     def _opts_dict(self):

@@ -132,9 +132,14 @@ int aens_nstats(void);
  * event_info = [[], True] (src/explicit_ode.pyx:212-216,239-259):
  *   __device__ double aens_time_events(double t, const double* y, const unsigned char* sw, const double* p);
  *                     next time event strictly after t, or AENS_NO_TIME_EVENT (the reference's None)
- *   __device__ int    aens_handle_time_event(double t, double* y, unsigned char* sw, const double* p); */
+ *   __device__ int    aens_handle_time_event(double t, double* y, unsigned char* sw, const double* p);
+ * Optional, flag AENS_MODEL_RHS_H: the fused form hk = h * f(t, y) the explicit Runge-Kutta stages of the fast
+ * arithmetic build consume (a model whose f is a product with a parameter folds h into it once per step); the strict
+ * build never calls it:
+ *   __device__ void aens_rhs_h(double h, double t, const double* y, const unsigned char* sw, const double* p, double* hk); */
 #define AENS_MODEL_HAS_JAC 1
 #define AENS_MODEL_TIME_EVENTS 2
+#define AENS_MODEL_RHS_H 4
 #define AENS_NO_TIME_EVENT (1.0e300 * 1.0e300) /* +inf */
 int aens_set_model_builtin(aens_handle_t *h, const char *name);
 /* has_jac: 0/1 as before, or a bit set of AENS_MODEL_* flags */

@@ -89,6 +89,15 @@ def test_nvrtc_compiles_user_models_for_sm_100a():
     for strict in (False, True):
         size = _core.nvrtc_check(USER_SRC, 2, 2, 1, 1, True, strict)
         assert size > 10000
+    # flag AENS_MODEL_RHS_H: the fused hk = h * f hook must exist when announced, and is compiled in when it does
+    fused = USER_SRC + """
+__device__ void aens_rhs_h(double h, double t, const double* y, const unsigned char* sw, const double* p, double* hk) {
+    double yd[2]; aens_rhs(t, y, sw, p, yd); hk[0] = h * yd[0]; hk[1] = h * yd[1];
+}
+"""
+    assert _core.nvrtc_check(fused, 2, 2, 1, 1, 1 | _core.MODEL_RHS_H, False) > 10000
+    with pytest.raises(_core.AensError, match="aens_rhs_h"):
+        _core.nvrtc_check(USER_SRC, 2, 2, 1, 1, 1 | _core.MODEL_RHS_H, False)
     with pytest.raises(_core.AensError) as e:
         _core.nvrtc_check("__device__ void aens_rhs(double t) { this is not C }", 2, 1)
     assert e.value.code == -3 and "user_model.cu" in str(e.value)

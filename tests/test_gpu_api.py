@@ -628,3 +628,38 @@ def test_first_passage_time_statistics_on_device():
     assert done["count"] == N - hit.sum() and done["min"] == done["max"] == 3.0
     none = sim.end_time_statistics(status=-2)
     assert none["count"] == 0 and np.isnan(none["mean"])
+
+
+def test_fused_step_times_rhs_hook_of_user_models():
+    """AENS_MODEL_RHS_H: a user model may supply hk = h * f(t, y) (the built-in Van der Pol model does); the fast Dopri5
+    build consumes it in its stages, the strict build never calls it.  Same expressions as the built-in model =>
+    identical doubles; and the fused form stays within the fast build's tolerance of the unfused one."""
+    from assimulo_b200.gpu import Batched_Explicit_Problem, Dopri5
+    src = VDP_SRC + r"""
+    __device__ void aens_rhs_h(double h, double t, const double* y, const unsigned char* sw, const double* p, double* hk) {
+        const double hmu = h * p[0];
+        hk[0] = h * y[1];
+        hk[1] = hmu * ((1. - y[0] * y[0]) * y[1] - y[0]);
+    }
+    """
+    y0, mu = cases.vdp_sweep(2000)
+    res = {}
+    for name, prob in (("builtin", dict(model="vdp")),
+                       ("fused", dict(source=src, n=2, n_p=1, has_jac=True, fused_rhs=True)),
+                       ("plain", dict(source=VDP_SRC, n=2, n_p=1, has_jac=True))):
+        sim = Dopri5(Batched_Explicit_Problem(y0=y0, p0=mu, **prob))
+        sim.rtol, sim.atol = 1e-6, 1e-6
+        sim.simulate(2.0)
+        res[name] = (sim.y.copy(), sim.statistics["nsteps"])
+    assert np.array_equal(res["fused"][0], res["builtin"][0]) and res["fused"][1] == res["builtin"][1]
+    assert rel_err(res["plain"][0], res["builtin"][0]) <= 1e-7
+    assert abs(res["plain"][1] - res["builtin"][1]) <= 0.001 * res["builtin"][1]
+    # strict arithmetic ignores the hook: reference operation order
+    st = []
+    for prob in (dict(model="vdp"), dict(source=src, n=2, n_p=1, has_jac=True, fused_rhs=True)):
+        sim = Dopri5(Batched_Explicit_Problem(y0=y0, p0=mu, **prob))
+        sim.arith = "strict"
+        sim.simulate(2.0)
+        st.append(sim.y.copy())
+    o = O.simulate("vdp", "Dopri5", y0, mu, tf=2.0, rtol=1e-6, atol=1e-6)
+    assert np.array_equal(st[0], st[1]) and rel_err(st[0], o["y"]) <= 1e-9   # pow ulps, see DESIGN section 7
