@@ -59,14 +59,18 @@ AENS_DEV float fpow(float x, float e) { return fex2(e * flg2(x)); }
 /* the argument of larger magnitude, decided on the high words (sign, exponent, 20 mantissa bits): when they tie the
  * two magnitudes agree to 2^-20, which is all a tolerance scale needs; keeps the compare off the fp64 pipe */
 AENS_DEV double absmax_hi(double a, double b) {
-    return ((__double2hiint(a) & 0x7fffffff) >= (__double2hiint(b) & 0x7fffffff)) ? a : b;
+    /* the high words compared as fp32 magnitudes: for finite non-tiny doubles the float with the same bit pattern
+     * orders like the 31-bit integer, and |.| is a free operand modifier (one FSETP instead of two masks + ISETP) */
+    return (fabsf(__int_as_float(__double2hiint(a))) >= fabsf(__int_as_float(__double2hiint(b)))) ? a : b;
 }
 /* MUFU.RCP64H seed of 1/b (~2^-23 relative) for the error norms: a perturbation of the tolerance scale, far below
  * what an accept/reject decision can see; r_recip() adds one Newton step (2^-46) where a quotient feeds a state */
 AENS_DEV double rcp_seed(double b) {
     double r;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b));
-    return r;
+    /* the instruction defines the low word as zero, which costs a move per use; any low word is as good (2^-20 of the
+     * seed's own 2^-23 error budget... i.e. 2^-20 relative at most), so the operand's is kept in place */
+    return __hiloint2double(__double2hiint(r), __double2loint(b));
 }
 #endif
 
@@ -498,6 +502,7 @@ struct Euler {
     bool needjac, curjac;
 
     AENS_DEV void seg_end() {}
+    AENS_DEV void late_status(const aens_args_t &) {}
     AENS_DEV void load_aux(const aens_args_t &a, long long idx) {
         inith = a.aux[idx];
         /* a fresh solver object: _needjac = True (euler.pyx:89).  The reference keeps its Jacobian across
@@ -674,6 +679,7 @@ struct RK4 {
     double h6;                /* h / 6. of the current h: the fp64 division runs only when h changes (last step), and
                                * yields the same double as recomputing it every step like the reference does */
     AENS_DEV void seg_end() {}
+    AENS_DEV void late_status(const aens_args_t &) {}
     AENS_DEV void load_aux(const aens_args_t &, long long) {}
     AENS_DEV void store_aux(const aens_args_t &, long long) {}
     AENS_DEV void interp(double, double *) {}
@@ -724,6 +730,7 @@ struct RK34 {
     int it;
 
     AENS_DEV void seg_end() {}
+    AENS_DEV void late_status(const aens_args_t &) {}
     AENS_DEV void load_aux(const aens_args_t &, long long) {}
     AENS_DEV void store_aux(const aens_args_t &, long long) {}
     AENS_DEV void interp(double time, double *out) { /* Hermite, runge_kutta.py:715-720; f_high = Y1 */
@@ -881,12 +888,21 @@ struct Dopri5 {
         }
     }
 
+    /* attempt_fast() leaves the hot loop with AENS_R_ERROR and no status: which of the two limits it was is decided
+     * here, once, instead of by predicated instructions in every attempt (dopri5.f:405-410) */
+    AENS_DEV void late_status(const aens_args_t &a) {
+        if (L.status == AENS_ST_COMPLETE) L.status = (nstep > a.o.maxsteps) ? AENS_ST_MAXSTEPS : AENS_ST_STEP_TOO_SMALL;
+    }
+    /* The hot loop without events and dense output (FAST) counts in its accept block only: naccpt, and in nrej the
+     * number of attempts that preceded the first accepted one (NREJCT leaves those out, dopri5.f:528); NREJCT then
+     * follows from NSTEP when the call returns. */
+    static constexpr bool COUNT_IN_ACCEPT_ONLY = !AENS_STRICT && M::NG == 0 && !DENSE;
     /* called by the kernel whenever attempt() returned anything but CONTINUE, i.e. when dopri5() returns:
      * NSTEP / NACCPT / NREJCT / NFCN of this call -> the member's statistics (runge_kutta.py:183-186) */
     AENS_DEV void seg_end() {
         L.st[AENS_STAT_NSTEPSTOTAL] += nstep;
         L.st[AENS_STAT_NSTEPS] += naccpt;
-        L.st[AENS_STAT_NERRFAILS] += nrej;
+        L.st[AENS_STAT_NERRFAILS] += COUNT_IN_ACCEPT_ONLY ? (naccpt ? nstep - naccpt - nrej : 0) : nrej;
         L.st[AENS_STAT_NFCNS] += 6 * nstep;
     }
 
@@ -980,12 +996,13 @@ struct Dopri5 {
         last = over;
     }
     /* dopri5.f:409 `0.1 |h| <= |x| uround` (uround = 2.3e-16, i.e. |h| <= |x| 2^-48.6), tested on the exponents only:
-     * exponent(h) + 50 <= exponent(x) implies |h| < |x| 2^-49, so every member flagged here is also flagged by the
-     * reference; one whose h sits within a factor 2 above that is flagged an attempt or two later, after the
+     * |h| 2^50 <= |x| (1 + 2^-20) implies 0.1 |h| <= |x| uround, so every member flagged here is also flagged by the
+     * reference; one whose h sits within a factor 2.6 above that is flagged an attempt or two later, after the
      * controller has shrunk h once more.  Keeps the test off the fp64 pipe. */
     AENS_DEV bool step_too_small(double x) const {
-        const int eh = (__double2hiint(h) >> 20) & 0x7ff, ex = (__double2hiint(x) >> 20) & 0x7ff;
-        return eh + 50 <= ex;
+        /* high words as integers: hi(h 2^50) = hi(h) + (50 << 20) exactly, and the high word is monotone in the
+         * magnitude, so this is |h| 2^50 <= |x| decided on the top 52 bits (h > 0: forward integration only) */
+        return __double2hiint(h) + (50 << 20) <= (__double2hiint(x) & 0x7fffffff);
     }
 #endif
 
@@ -1133,11 +1150,7 @@ struct Dopri5 {
         using dp::T;
         using dp::uround;
         const double x = L.t;
-        const bool small = step_too_small(x);
-        if ((nstep > a.o.maxsteps) | small) { /* dopri5.f:405-410 */
-            L.status = (nstep > a.o.maxsteps) ? AENS_ST_MAXSTEPS : AENS_ST_STEP_TOO_SMALL;
-            return AENS_R_ERROR;
-        }
+        if ((nstep > a.o.maxsteps) | step_too_small(x)) return AENS_R_ERROR; /* status: late_status() */
         nstep += 1;
         /* the last step lands on the end point exactly: x + (xend - x) can miss xend by an ulp, which the
          * reference tolerates at tfinal (100 eps slack of the driver loop) but not at a time event, where the next
@@ -1270,16 +1283,19 @@ struct Dopri5 {
         const double h_step = h;
         clamp_next(nb, hnew, accept, true);
         if constexpr (M::NG == 0 && !DENSE) {
-            /* final-state-only members: commit by select, no divergent region in the hot loop */
-            naccpt += accept ? 1 : 0;
-            nrej += (!accept && naccpt >= 1) ? 1 : 0;
-            reject = accept ? 0 : 1;
+            /* final-state-only members: one short accept block (the compiler branches around the register moves of a
+             * select-commit anyway), nothing on the reject side */
+            if (accept) {
+                nrej = naccpt ? nrej : nstep - 1; /* see COUNT_IN_ACCEPT_ONLY */
+                naccpt += 1;
 #pragma unroll
-            for (int i = 0; i < N; ++i) {
-                k1[i] = accept ? k2[i] : k1[i];
-                L.y[i] = accept ? y1[i] : L.y[i];
+                for (int i = 0; i < N; ++i) {
+                    k1[i] = k2[i];
+                    L.y[i] = y1[i];
+                }
+                L.t = xph;
             }
-            L.t = accept ? xph : x;
+            reject = accept ? 0 : 1;
             return (accept && was_last) ? AENS_R_COMPLETE : AENS_R_CONTINUE;
         } else {
             if (accept) {
@@ -1396,6 +1412,7 @@ __device__ __forceinline__ void aens_run(const aens_args_t &a) {
                 r = s.attempt(a, idx);
             } while (__all_sync(stepmask, r == AENS_R_CONTINUE));
             if (r != AENS_R_CONTINUE) {
+                if (r == AENS_R_ERROR) s.late_status(a);
                 s.seg_end();
                 bool done = true;
                 if (r == AENS_R_EVENT) {

@@ -315,6 +315,7 @@ struct Radau5 {
     bool first, last, reject, new_jac_req, jac_is_fresh;
 
     AENS_DEV void seg_end() {}
+    AENS_DEV void late_status(const aens_args_t &) {}
     AENS_DEV void load_aux(const aens_args_t &, long long) {}
     AENS_DEV void store_aux(const aens_args_t &, long long) {}
 
@@ -721,6 +722,7 @@ struct Rodas {
     AENS_DEV void load_aux(const aens_args_t &, long long) {}
     AENS_DEV void store_aux(const aens_args_t &, long long) {}
     /* IWORK(14..19) -> statistics, rosenbrock.py:417-423 */
+    AENS_DEV void late_status(const aens_args_t &) {}
     AENS_DEV void seg_end() {
         L.st[AENS_STAT_NSTEPS] += naccpt;
         L.st[AENS_STAT_NFCNS] += nfcn;
