@@ -867,6 +867,8 @@ struct Dopri5 {
     double facold;             /* FACOLD */
 #else
     float lfacold;             /* beta/2 * lg2(max(err^2, 1e-8)): the controller works on lg2 of the squared norm */
+    float lfmin;               /* lower bound of lg2 fac for the next accepted step: lg2 facc2, or 0 after a rejection
+                                * ('a step after a rejection does not grow', dopri5.f:516) -- the REJECT flag as data */
 #endif
     double cont[DENSE ? 5 * N : 1], told, hstep;
     int nstep, naccpt, nrej;   /* per dopri5() call, i.e. per segment; flushed into L.st when the segment ends */
@@ -1013,6 +1015,7 @@ struct Dopri5 {
         facold = 1.0e-4;
 #else
         lfacold = a.ctl[5];
+        lfmin = a.ctl[4];
 #endif
         last = false;
         reject = false;
@@ -1275,7 +1278,7 @@ struct Dopri5 {
         const float l11 = fmaf(a.ctl[0], le2, a.ctl[2]);
         float lf = fminf(a.ctl[3], accept ? l11 - lfacold : l11);
         if (accept) {
-            lf = fmaxf(lf, reject ? 0.0f : a.ctl[4]);
+            lf = fmaxf(lf, lfmin);
             lfacold = a.ctl[1] * fmaxf(le2, a.ctl[6]); /* FACOLD = max(err, 1e-4) */
         }
         const double hnew = h * (double)fex2(-lf);
@@ -1295,7 +1298,7 @@ struct Dopri5 {
                 }
                 L.t = xph;
             }
-            reject = accept ? 0 : 1;
+            lfmin = accept ? a.ctl[4] : 0.0f;
             return (accept && was_last) ? AENS_R_COMPLETE : AENS_R_CONTINUE;
         } else {
             if (accept) {
@@ -1319,12 +1322,12 @@ struct Dopri5 {
                     k1[i] = k2[i];
                     L.y[i] = y1[i];
                 }
-                reject = 0;
+                lfmin = a.ctl[4];
                 const int flag = aens_post_step<M, Dopri5>(*this, L, a, idx, x, xph);
                 if (flag == AENS_R_EVENT) return AENS_R_EVENT;
                 if (was_last) return AENS_R_COMPLETE;
             } else {
-                reject = 1;
+                lfmin = 0.0f;
                 if (naccpt >= 1) nrej += 1;
             }
             return AENS_R_CONTINUE;
