@@ -663,3 +663,12 @@ def test_fused_step_times_rhs_hook_of_user_models():
         st.append(sim.y.copy())
     o = O.simulate("vdp", "Dopri5", y0, mu, tf=2.0, rtol=1e-6, atol=1e-6)
     assert np.array_equal(st[0], st[1]) and rel_err(st[0], o["y"]) <= 1e-9   # pow ulps, see DESIGN section 7
+
+
+def test_graft_entry_smoke_runs():
+    """the driver's round-end smoke check must keep working when the solver classes change"""
+    import importlib
+    import sys
+    sys.path.insert(0, ROOT)
+    g = importlib.import_module("__graft_entry__")
+    g.smoke()
