@@ -31,7 +31,8 @@ typedef struct {
      * caller's member-major arrays -- page-locked host memory mapped into the device address space, read over
      * PCIe by the warp that is about to integrate it -- instead of from the SoA state; the SoA state, the
      * parameters and the pristine copy for aens_reset are written from the fetched values.  out_* (each may be
-     * NULL) receive the final values, again member-major and straight into host memory. */
+     * NULL) receive the final values, again member-major and straight into host memory.  A parameter sweep whose
+     * members share one initial state passes that row by value (y0_shared / y0_row, aens_set_shared_y0). */
     const double *in_y;       /* [N][n] */
     const double *in_p;       /* [N][n_p] */
     const unsigned char *in_sw; /* [N][n_sw] */
@@ -53,6 +54,10 @@ typedef struct {
      * [5] beta/2 * lg2(1e-8)  (FACOLD = 1e-4 at segment start)  [6] lg2(1e-8)  [7] reserved */
     float ctl[8];
     aens_opts_t o;
+    /* (appended so that the offsets the hot loops read stay where they were) */
+    int zc;                   /* 1: zero-copy mode (the in_* / out_* pointers above are in use) */
+    int y0_shared;            /* zero-copy mode: every member starts from y0_row instead of a row of in_y */
+    double y0_row[AENS_MAX_N];
 } aens_args_t;
 
 #endif

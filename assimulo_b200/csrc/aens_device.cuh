@@ -163,8 +163,13 @@ struct Lane {
     }
 
     AENS_DEV void load(const aens_args_t &a, long long idx) {
-        if (a.in_y) { /* zero-copy fetch from the caller's member-major host arrays */
-            load_row<M::N>(a.in_y, idx, y);
+        if (a.zc) { /* zero-copy fetch from the caller's member-major host arrays */
+            if (a.y0_shared) {
+#pragma unroll
+                for (int i = 0; i < M::N; ++i) y[i] = a.y0_row[i];
+            } else {
+                load_row<M::N>(a.in_y, idx, y);
+            }
             t = a.t0;
 #pragma unroll
             for (int i = 0; i < M::N; ++i) a.y0_store[(long long)i * a.N + idx] = y[i];

@@ -76,6 +76,7 @@ cdef extern from "assimulo_cuda.h":
                            long long *n_not_complete) nogil
     int aens_get_summary(aens_handle_t *h, long long *sums, long long *n_not_complete) nogil
     int aens_set_host_mode(aens_handle_t *h, int mode) nogil
+    int aens_set_shared_y0(aens_handle_t *h, int on) nogil
     int aens_reduce_final(aens_handle_t *h, double *mean, double *var, double *mn, double *mx, long long *count) nogil
     int aens_reduce_end_times(aens_handle_t *h, int status, double *mean, double *var, double *mn, double *mx,
                               long long *count) nogil
@@ -230,15 +231,34 @@ cdef class Handle:
         self._check(rc)
         self._dims()
 
-    def set_ensemble(self, y0, p=None, sw0=None, double t0=0.0):
-        cdef np.ndarray[double, ndim=2, mode="c"] y = np.ascontiguousarray(y0, dtype=np.float64)
+    def _shared_row(self, y0, p, sw0, N):
+        """y0 given as ONE row [n] shared by all members (aens_set_shared_y0): returns (y0 as [1, n], N) with N taken
+        from p / sw0 / the N argument; (y0 as [N, n], N) otherwise."""
+        y = np.ascontiguousarray(y0, dtype=np.float64)
+        if y.ndim != 1:
+            if y.ndim != 2:
+                raise ValueError("y0 must have shape [N, n] or [n]")
+            self._check(aens_set_shared_y0(self.h, 0))
+            return y, len(y)
+        if N is None:   # (this module is compiled without bounds checks: no blind indexing of shape tuples)
+            shp = np.shape(p) if (self.n_p and p is not None) else np.shape(sw0) if (self.n_sw and sw0 is not None) else ()
+            if len(shp) != 2:
+                raise ValueError("a shared y0 row needs a 2-D p or sw0, or N=, to fix the ensemble size")
+            N = shp[0]
+        self._check(aens_set_shared_y0(self.h, 1))
+        return y.reshape(1, -1), int(N)
+
+    def set_ensemble(self, y0, p=None, sw0=None, double t0=0.0, N=None):
+        cdef np.ndarray[double, ndim=2, mode="c"] y
         cdef np.ndarray[double, ndim=2, mode="c"] pp
         cdef np.ndarray[np.uint8_t, ndim=2, mode="c"] ss
         cdef const double *pptr = NULL
         cdef const unsigned char *sptr = NULL
-        cdef long long N = y.shape[0]
+        cdef long long N_
+        y, N_ = self._shared_row(y0, p, sw0, N)
+        N = N_
         if y.shape[1] != self.n:
-            raise ValueError("y0 must have shape [N, %d]" % self.n)
+            raise ValueError("y0 must have shape [N, %d] or [%d]" % (self.n, self.n))
         if self.n_p:
             pp = np.ascontiguousarray(p, dtype=np.float64)
             if pp.shape[0] != N or pp.shape[1] != self.n_p:
@@ -252,9 +272,10 @@ cdef class Handle:
         cdef const double *yptr = &y[0, 0]
         cdef int rc
         with nogil:
-            rc = aens_set_ensemble(self.h, N, yptr, pptr, sptr, t0)
+            rc = aens_set_ensemble(self.h, N_, yptr, pptr, sptr, t0)
+        aens_set_shared_y0(self.h, 0)
         self._check(rc)
-        self.N = N
+        self.N = N_
         self.n_out = 0
 
     def reset(self):
@@ -326,18 +347,21 @@ cdef class Handle:
         self._check(aens_set_fetch_reverse(self.h, reverse))
 
     def simulate_host(self, y0, p, sw0, double t0, double tfinal, out_y=None, out_t=None, out_sw=None,
-                      out_status=None, int nchunks=8):
+                      out_status=None, int nchunks=8, N=None):
         """aens_simulate_host: upload, integrate and download in one chunk-pipelined call.  y0/p/sw0 as for
         set_ensemble; out_* are caller-owned C-contiguous arrays (ideally pinned_empty) or None to skip that
-        result.  Returns (statistic sums dict, number of members that did not complete)."""
-        cdef np.ndarray[double, ndim=2, mode="c"] y = np.ascontiguousarray(y0, dtype=np.float64)
+        result.  A 1-D y0 is ONE row shared by all members (only p / sw0 cross PCIe then).  Returns (statistic sums
+        dict, number of members that did not complete)."""
+        cdef np.ndarray[double, ndim=2, mode="c"] y
         cdef np.ndarray[double, ndim=2, mode="c"] pp
         cdef np.ndarray[np.uint8_t, ndim=2, mode="c"] ss
         cdef const double *pptr = NULL
         cdef const unsigned char *sptr = NULL
-        cdef long long N = y.shape[0]
+        cdef long long N_
+        y, N_ = self._shared_row(y0, p, sw0, N)
+        N = N_
         if y.shape[1] != self.n:
-            raise ValueError("y0 must have shape [N, %d]" % self.n)
+            raise ValueError("y0 must have shape [N, %d] or [%d]" % (self.n, self.n))
         if self.n_p:
             pp = np.ascontiguousarray(p, dtype=np.float64)
             if pp.shape[0] != N or pp.shape[1] != self.n_p:
@@ -374,7 +398,8 @@ cdef class Handle:
         cdef long long nbad = 0
         cdef int rc
         with nogil:
-            rc = aens_simulate_host(self.h, N, yptr, pptr, sptr, t0, tfinal, yo, to, so, sto, nchunks, sums, &nbad)
+            rc = aens_simulate_host(self.h, N_, yptr, pptr, sptr, t0, tfinal, yo, to, so, sto, nchunks, sums, &nbad)
+        aens_set_shared_y0(self.h, 0)
         self._check(rc)
         self.N = N
         self.n_out = 0

@@ -77,6 +77,9 @@ class Batched_Explicit_Problem(object):
         if y0.shape[-1] != self.n or y0.ndim > 2:
             raise AssimuloException("y0 must have shape [n] or [N, n] with n = %d." % self.n)
         self.N = N
+        #: the one initial state all members share, when y0 was given as a single row (a pure parameter sweep): the
+        #: solvers then pass this row instead of [N, n] to the device (aens_set_shared_y0)
+        self.y0_row = y0.reshape(-1).copy() if (y0.size == self.n and N > 1) else None
         self.y0 = np.ascontiguousarray(np.broadcast_to(y0.reshape(-1, self.n) if y0.ndim == 2 else y0[None, :],
                                                        (N, self.n)))
         if self.n_p:

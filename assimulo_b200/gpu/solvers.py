@@ -80,6 +80,7 @@ class Batched_Explicit_ODE(object):
         self.t = problem.t0
         self.N = problem.N
         self.y = problem.y0.copy()
+        self._y_row = problem.y0_row   # set while every member still sits at one shared initial state
         self.sw = problem.sw0.astype(bool)
         self._status = None        # per-member arrays are materialised on first access (see the properties)
         self._t_members = None
@@ -134,7 +135,13 @@ class Batched_Explicit_ODE(object):
             raise Explicit_ODE_Exception("y0 must be of the same length as the original problem.")
         self.t = float(t0)
         # no defensive copies of ensemble-sized arrays: they are only read when uploaded to the device
-        self.y = np.ascontiguousarray(np.broadcast_to(y0.reshape(-1, self._leny), (self.N, self._leny)))
+        self._y_row = y0.reshape(-1).copy() if (y0.size == self._leny and self.N > 1) else None
+        if self._y_row is not None:   # one shared initial state: a stride-0 view, nothing ensemble-sized is built
+            self.y = np.broadcast_to(self._y_row, (self.N, self._leny))
+        else:
+            self.y = np.ascontiguousarray(y0.reshape(-1, self._leny))
+            if self.y.shape[0] != self.N:
+                raise Explicit_ODE_Exception("y0 must have shape [n] or [N, n] with N = %d." % self.N)
         if sw0 is not None:
             self.sw = np.ascontiguousarray(np.broadcast_to(np.asarray(sw0, dtype=bool).reshape(-1, self.problem.n_sw),
                                                            (self.N, self.problem.n_sw)))
@@ -143,7 +150,8 @@ class Batched_Explicit_ODE(object):
         self._dirty = True
 
     def reset(self):
-        self.re_init(self.problem.t0, self.problem.y0, self.problem.sw0 if self.problem.n_sw else None)
+        y0 = self.problem.y0_row if self.problem.y0_row is not None else self.problem.y0
+        self.re_init(self.problem.t0, y0, self.problem.sw0 if self.problem.n_sw else None)
 
     def initialize(self):
         self.statistics.reset()
@@ -209,9 +217,12 @@ class Batched_Explicit_ODE(object):
             h.set_schedule(int(self.options["refill_threshold"]), None)
             y = pin[1] if pin is not None else np.empty((self.N, self._leny))
             sw = np.empty((self.N, self.problem.n_sw), dtype=np.uint8) if self.problem.n_sw else None
-            sums, nbad = h.simulate_host(self.y, self.problem.p0 if self.problem.n_p else None,
+            # a sweep whose members share one initial state sends that row, not [N, n] (aens_set_shared_y0)
+            y_in = self._y_row if self._y_row is not None else self.y
+            sums, nbad = h.simulate_host(y_in, self.problem.p0 if self.problem.n_p else None,
                                          self.sw.astype(np.uint8) if self.problem.n_sw else None, self.t, tfinal,
-                                         out_y=y, out_sw=sw, nchunks=int(nch))
+                                         out_y=y, out_sw=sw, nchunks=int(nch), N=self.N)
+            self._y_row = None
             self._dirty = False
             self._launched = True
             self.elapsed_kernel_ms = None
@@ -219,9 +230,11 @@ class Batched_Explicit_ODE(object):
             self._status, self._t_members, self._events = None, None, None
         else:
             if self._dirty:
-                h.set_ensemble(self.y, self.problem.p0 if self.problem.n_p else None,
-                               self.sw.astype(np.uint8) if self.problem.n_sw else None, self.t)
+                h.set_ensemble(self._y_row if self._y_row is not None else self.y,
+                               self.problem.p0 if self.problem.n_p else None,
+                               self.sw.astype(np.uint8) if self.problem.n_sw else None, self.t, N=self.N)
                 self._dirty = False
+            self._y_row = None
             reduce_rows = bool(self.options["reduce_rows"]) and output_list is not None
             if reduce_rows != getattr(self, "_reducing", False):
                 h.set_output(None, int(self.options["event_slots"]))  # the mode is switched with no grid set

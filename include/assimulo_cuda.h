@@ -194,6 +194,10 @@ int aens_simulate_host(aens_handle_t *h, long long N, const double *y0, const do
  * fetch them and write the final rows back when they finish; otherwise the chunked staging pipeline),
  * 1 = always the chunked staging pipeline, 2 = zero-copy or fail. */
 int aens_set_host_mode(aens_handle_t *h, int mode);
+/* Parameter sweeps whose members share one initial state (every Explicit_Problem of the loop built with the same
+ * y0): with on != 0 the y0 argument of aens_set_ensemble / aens_simulate_host is ONE row y0[n] instead of
+ * y0[N][n]; in zero-copy mode the row travels in the kernel's argument block, so only p (and sw0) cross PCIe. */
+int aens_set_shared_y0(aens_handle_t *h, int on);
 /* statistic totals and the number of members that did not complete, after aens_simulate */
 int aens_get_summary(aens_handle_t *h, long long *sums /*[AENS_NSTATS]*/, long long *n_not_complete);
 

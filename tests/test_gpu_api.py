@@ -672,3 +672,42 @@ def test_graft_entry_smoke_runs():
     sys.path.insert(0, ROOT)
     g = importlib.import_module("__graft_entry__")
     g.smoke()
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_shared_initial_state_row_equals_the_expanded_array(mode):
+    """aens_set_shared_y0: a parameter sweep gives y0 as ONE row; results are identical to passing [N, n] -- through the
+    solver class (host pipeline: zero-copy and chunked staging; set_ensemble path with an output grid), reset() and
+    re_init() included."""
+    from assimulo_b200.gpu import Batched_Explicit_Problem, Dopri5, _core
+    N = 3001
+    _, mu = cases.vdp_sweep(N)
+    mu_p = _core.pinned_empty((N, 1))
+    mu_p[:] = mu
+    full = Dopri5(Batched_Explicit_Problem(model="vdp", y0=np.tile([2.0, -0.6], (N, 1)), p0=mu_p))
+    row = Dopri5(Batched_Explicit_Problem(model="vdp", y0=[2.0, -0.6], p0=mu_p))
+    assert row.problem.y0_row is not None and full.problem.y0_row is None and row.y.shape == (N, 2)
+    for s in (full, row):
+        s.options["reuse_buffers"] = True      # pinned result buffers: zero-copy mode is possible
+    row._get_handle().set_host_mode(mode)      # (the expanded array of `full` is pageable: automatic mode)
+    yf = np.array(full.simulate(2.0)[1][-1])
+    yr = np.array(row.simulate(2.0)[1][-1])
+    assert np.array_equal(yf, yr) and full.statistics["nsteps"] == row.statistics["nsteps"]
+    row.reset()
+    assert row._y_row is not None and np.array_equal(row.y, np.tile([2.0, -0.6], (N, 1)))
+    assert np.array_equal(np.array(row.simulate(2.0)[1][-1]), yf)
+    # with an output grid the ensemble goes through aens_set_ensemble: the row is expanded on the device
+    row.reset(); full.reset()
+    tr, dr = row.simulate(2.0, 4)
+    tf_, df = full.simulate(2.0, 4)
+    assert np.array_equal(np.array(dr)[1:], np.array(df)[1:])
+    # re_init with another shared row, and with a full array
+    row.re_init(0.0, [1.0, 0.0]); full.re_init(0.0, np.tile([1.0, 0.0], (N, 1)))
+    assert np.array_equal(np.array(row.simulate(1.0)[1][-1]), np.array(full.simulate(1.0)[1][-1]))
+    # raw handle: 1-D y0 needs something that fixes N
+    h = _core.Handle(0)
+    h.set_model_builtin("linear")
+    with pytest.raises(ValueError):
+        h.set_ensemble(np.array([1.0]), None)
+    h.set_ensemble(np.array([4.0]), np.tile([-1.0, 0.0, 0.0], (5, 1)))
+    assert h.N == 5
