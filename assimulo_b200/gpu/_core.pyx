@@ -55,6 +55,7 @@ cdef extern from "assimulo_cuda.h":
     int aens_simulate_async(aens_handle_t *h, double tfinal) nogil
     int aens_sync(aens_handle_t *h) nogil
     int aens_last_kernel_ms(aens_handle_t *h, float *ms) nogil
+    int aens_kernel_ms_history(aens_handle_t *h, float *ms, int n) nogil
     int aens_get_final(aens_handle_t *h, double *t, double *y, unsigned char *sw, int *status) nogil
     int aens_get_stats(aens_handle_t *h, int which, int *out) nogil
     int aens_get_stats_sum(aens_handle_t *h, long long *sums) nogil
@@ -473,6 +474,17 @@ cdef class Handle:
         cdef float ms = 0
         self._check(aens_last_kernel_ms(self.h, &ms))
         return ms
+
+    def kernel_ms_history(self, int n=64):
+        """durations (ms) of the most recent integration-kernel launches, newest first (at most 64)"""
+        cdef float ms[64]
+        cdef int k
+        if n > 64:
+            n = 64
+        with nogil:
+            k = aens_kernel_ms_history(self.h, ms, n)
+        self._check(k)
+        return [ms[i] for i in range(k)]
 
     def get_final(self, bint want_y=True, bint want_sw=True, bint want_t=True, out_t=None, out_y=None,
                   out_status=None):

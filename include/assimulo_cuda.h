@@ -178,6 +178,10 @@ int aens_simulate_async(aens_handle_t *h, double tfinal);
 int aens_sync(aens_handle_t *h);
 /* device time of the last aens_simulate[_async] launch in milliseconds (CUDA events on the handle's stream) */
 int aens_last_kernel_ms(aens_handle_t *h, float *ms);
+/* Durations of the most recent integration-kernel launches, newest first (each launch records its own CUDA event
+ * pair on the launching stream; the ring keeps 64): lets a caller that queued launches back to back with
+ * aens_simulate_async read every kernel's time afterwards.  Synchronises the stream; returns how many were written. */
+int aens_kernel_ms_history(aens_handle_t *h, float *ms, int n);
 
 /* aens_set_ensemble + aens_simulate + aens_get_final in ONE call for inputs and results in host memory -- what a
  * Python loop `for i: Solver(Explicit_Problem(rhs_i, y0_i)).simulate(tfinal)` does, end to end.  The members are

@@ -711,3 +711,23 @@ def test_shared_initial_state_row_equals_the_expanded_array(mode):
         h.set_ensemble(np.array([1.0]), None)
     h.set_ensemble(np.array([4.0]), np.tile([-1.0, 0.0, 0.0], (5, 1)))
     assert h.N == 5
+
+
+def test_kernel_time_history_of_queued_launches():
+    """aens_kernel_ms_history: every launch records its own event pair, so launches queued back to back with
+    simulate_async can be timed individually afterwards (bench.py's roofline uses the launches of its timed region)."""
+    from assimulo_b200.gpu import _core
+    y0, mu = cases.vdp_sweep(1 << 16)
+    h = _core.Handle(0)
+    h.set_model_builtin("vdp")
+    h.set_ensemble(y0, mu, None, 0.0)
+    h.set_opts({"solver": _core.SOLVER_IDS["Dopri5"], "rtol": 1e-6, "atol": 1e-6})
+    assert h.kernel_ms_history() == []
+    for _ in range(3):
+        h.reset()
+        h.simulate_async(2.0)
+    h.sync()
+    ms = h.kernel_ms_history()
+    assert len(ms) == 3 and all(m > 0 for m in ms) and ms[0] == h.last_kernel_ms()
+    assert max(ms) < 3 * min(ms)
+    assert len(h.kernel_ms_history(2)) == 2
