@@ -201,7 +201,20 @@ struct Lane {
         M::prep(p);
 #endif
     }
+    /* FILL_ROWS (kernels that store dense-output rows): the rows this member never reached -- it failed, was
+     * terminated, or the grid extends beyond this call's tfinal -- are set to NaN here, by the member itself, instead
+     * of pre-filling the whole [rows][n][N] buffer before every launch (40 GB for config 5) */
+    template <bool FILL_ROWS>
     AENS_DEV void store(const aens_args_t &a, long long idx) {
+        if constexpr (FILL_ROWS) {
+            if (a.dense) {
+                const double qnan = __longlong_as_double(0x7ff8000000000000ll);
+                for (int k = gi; k < a.n_grid; ++k) {
+#pragma unroll
+                    for (int i = 0; i < M::N; ++i) a.dense[((long long)k * M::N + i) * a.N + idx] = qnan;
+                }
+            }
+        }
         a.t[idx] = t;
 #pragma unroll
         for (int i = 0; i < M::N; ++i) a.y[(long long)i * a.N + idx] = y[i];
@@ -1377,7 +1390,7 @@ __device__ __forceinline__ void aens_run(const aens_args_t &a) {
                  * together hold consecutive members, so their rows form contiguous blocks (SoA state in HBM and, in
                  * zero-copy mode, the caller's member-major host arrays) */
                 if (pending) {
-                    s.L.store(a, idx);
+                    s.L.template store<S::HAS_DENSE && !S::REDUCE>(a, idx);
                     s.store_aux(a, idx);
                     pending = false;
                 }
@@ -1471,7 +1484,7 @@ __device__ __forceinline__ void aens_run(const aens_args_t &a) {
         }
     }
     if (pending) { /* the warp's last members: every lane is idle here */
-        s.L.store(a, idx);
+        s.L.template store<S::HAS_DENSE && !S::REDUCE>(a, idx);
         s.store_aux(a, idx);
     }
 }

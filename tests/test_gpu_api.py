@@ -731,3 +731,35 @@ def test_kernel_time_history_of_queued_launches():
     assert len(ms) == 3 and all(m > 0 for m in ms) and ms[0] == h.last_kernel_ms()
     assert max(ms) < 3 * min(ms)
     assert len(h.kernel_ms_history(2)) == 2
+
+
+def test_unreached_rows_are_nan_and_survive_a_continuation_call():
+    """Rows of the output grid a member has not reached are NaN (written by the member itself when it is stored, no
+    pre-fill of the buffer); a second aens_simulate on the same grid continues and fills them, keeping the earlier rows."""
+    from assimulo_b200.gpu import _core
+    N = 1000
+    y0, mu = cases.vdp_sweep(N)
+    grid = np.linspace(0.0, 2.0, 9)[1:]
+    h = _core.Handle(0)
+    h.set_model_builtin("vdp")
+    h.set_ensemble(y0, mu, None, 0.0)
+    h.set_opts({"solver": _core.SOLVER_IDS["Dopri5"], "rtol": 1e-6, "atol": 1e-6})
+    h.set_output(grid, 16)
+    h.simulate(1.0)
+    d1 = h.get_dense().copy()
+    assert np.isfinite(d1[:4]).all() and np.isnan(d1[4:]).all()
+    h.simulate(2.0)
+    d2 = h.get_dense()
+    assert np.isfinite(d2).all() and np.array_equal(d2[:4], d1[:4])
+    o = O.simulate("vdp", "Dopri5", y0, mu, tf=2.0, t_grid=grid, rtol=1e-6, atol=1e-6)
+    assert rel_err(np.transpose(d2, (1, 0, 2)), o["dense"]) <= 1e-4   # the restart at t = 1 changes the step sequence
+    # members that fail early leave NaN rows behind
+    h.reset()
+    h.set_opts({"solver": _core.SOLVER_IDS["Dopri5"], "rtol": 1e-6, "atol": 1e-6, "maxsteps": 40})
+    h.set_output(grid, 16)
+    h.simulate(2.0)
+    t, _, _, st = h.get_final()
+    d3 = h.get_dense()
+    assert (st != 0).any() and (st == 0).any()
+    for k, tk in enumerate(grid):
+        assert np.array_equal(np.isfinite(d3[k][:, 0]), t >= tk)
