@@ -851,6 +851,7 @@ struct Tab {
     double a21, a31, a32, a41, a42, a43, a51, a52, a53, a54, a61, a62, a63, a64, a65, a71, a73, a74, a75, a76;
     double e1, e3, e4, e5, e6, e7;
     double d1, d3, d4, d5, d6, d7;
+    double inv101; /* 1/1.01 of the end-point test (as a literal it costs two UMOVs per attempt) */
 };
 static __constant__ Tab T = {
     0.2, 0.3, 0.8, 8.0 / 9.0,
@@ -859,7 +860,8 @@ static __constant__ Tab T = {
     -5103.0 / 18656.0, 35.0 / 384.0, 500.0 / 1113.0, 125.0 / 192.0, -2187.0 / 6784.0, 11.0 / 84.0,
     71.0 / 57600.0, -71.0 / 16695.0, 71.0 / 1920.0, -17253.0 / 339200.0, 22.0 / 525.0, -1.0 / 40.0,
     -12715105075.0 / 11282082432.0, 87487479700.0 / 32700410799.0, -10690763975.0 / 1880347072.0,
-    701980252875.0 / 199316789632.0, -1453857185.0 / 822651844.0, 69997945.0 / 29380423.0};
+    701980252875.0 / 199316789632.0, -1453857185.0 / 822651844.0, 69997945.0 / 29380423.0,
+    1.0 / 1.01};
 constexpr double uround = 2.3e-16; /* dopri5.f:253-254 */
 }  // namespace dp
 
@@ -1001,7 +1003,7 @@ struct Dopri5 {
     AENS_DEV Bounds next_bounds(const aens_args_t &a, double xn) const {
         Bounds b;
         b.rem = L.tend(a) - xn;
-        b.b101 = b.rem * (1.0 / 1.01);
+        b.b101 = b.rem * dp::T.inv101;
         return b;
     }
     /* Both magnitude tests look at the high words only (positive doubles order like their bit patterns; a tie of
