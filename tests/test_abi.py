@@ -113,3 +113,14 @@ def test_opts_struct_layout_matches_header():
     assert o.i[0] == 3 and o.i[2] == 100000 and o.rtol == 1e-6 and o.atol[15] == 1e-6
     assert list(o.rest)[:6] == [0.01, 0.0, 0.0, 0.9, 0.2, 10.0]
     assert lib.aens_default_opts(99, C.byref(o)) == -1
+
+
+def test_every_entry_point_is_documented_in_integration_md():
+    """INTEGRATION.md section 1 maps each C entry point to the reference interface it replaces: none may be missing."""
+    import re
+    hdr = open(os.path.join(ROOT, "include", "assimulo_cuda.h")).read()
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    names = set(re.findall(r"^[a-z][^\n(]*?\**(aens_[a-z0-9_]+)\(", hdr, flags=re.M))
+    assert len(names) > 30
+    missing = sorted(n for n in names if n not in doc)
+    assert not missing, missing
