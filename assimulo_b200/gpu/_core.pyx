@@ -1,4 +1,4 @@
-# cython: language_level=3, boundscheck=False, wraparound=False
+# cython: language_level=3, boundscheck=True, wraparound=False
 """Cython host binding of libassimulo_cuda.so (include/assimulo_cuda.h).
 
 Plays the role ``thirdparty/radau5/radau5ode.pyx`` (RadauMemory + radau5_py_solve) and the f2py module
@@ -241,7 +241,7 @@ cdef class Handle:
                 raise ValueError("y0 must have shape [N, n] or [n]")
             self._check(aens_set_shared_y0(self.h, 0))
             return y, len(y)
-        if N is None:   # (this module is compiled without bounds checks: no blind indexing of shape tuples)
+        if N is None:
             shp = np.shape(p) if (self.n_p and p is not None) else np.shape(sw0) if (self.n_sw and sw0 is not None) else ()
             if len(shp) != 2:
                 raise ValueError("a shared y0 row needs a 2-D p or sw0, or N=, to fix the ensemble size")
