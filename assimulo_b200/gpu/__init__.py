@@ -8,7 +8,7 @@
 Importing this package does not need a GPU; creating a solver's device handle does (no CPU fallback).
 """
 from .exception import (AssimuloException, Dopri5_Exception, Explicit_ODE_Exception, Radau5Error,  # noqa: F401
-                        Radau_Exception, Rodas_Exception, TerminateSimulation)
+                        Radau_Exception, Rodas_Exception, TerminateSimulation, TimeLimitExceeded)
 from .problem import BUILTIN_MODELS, Batched_Explicit_Problem  # noqa: F401
 from .solvers import (Batched_Explicit_ODE, Dopri5, ExplicitEuler, ImplicitEuler, Radau5ODE,  # noqa: F401
                       RodasODE, RungeKutta4, RungeKutta34)
