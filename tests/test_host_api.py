@@ -180,3 +180,27 @@ def test_empty_and_misshapen_ensembles_are_rejected_up_front():
     with pytest.raises(AssimuloException, match="shape"):
         Batched_Explicit_Problem(model="vdp", y0=np.zeros((5, 3)))
     assert Batched_Explicit_Problem(model="vdp", y0=[2.0, -0.6], N=7).y0.shape == (7, 2)
+
+
+def test_committed_bench_line_carries_the_contract_keys():
+    """profiles/r1_bench.json is the JSON line bench.py printed on the B200: every key the measurement contract names."""
+    import json
+    import os
+    from conftest import ROOT
+    lines = [l for l in open(os.path.join(ROOT, "profiles", "r1_bench.json")) if l.strip().startswith("{")]
+    assert len(lines) == 1                                   # exactly ONE JSON line on stdout
+    d = json.loads(lines[0])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches", "roofline", "cpu_baseline", "clocks"):
+        assert k in d, k
+    assert d["n_gpus"] == 1 and d["warmup"] >= 3 and d["higher_is_better"] is True and d["scaling"] == "weak"
+    assert d["dtype"] == "f64" and d["data"] == "synthetic" and d["vs_baseline"] is None and "workload" in d["config"]
+    assert set(("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step")) <= set(d["e2e"])
+    assert d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["d2h_bytes_per_step"] > 0 and d["e2e"]["value"] < d["value"]
+    r = d["roofline"]
+    assert set(("bound", "achieved", "peak", "unit", "frac", "traffic")) <= set(r)
+    assert abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-12 and 0.5 < r["frac"] < 1.0 and r["traffic"] > 0
+    c = d["cpu_baseline"]
+    assert set(("value", "unit", "cores", "kind", "sample")) <= set(c) and c["kind"] in ("reference", "port")
+    assert d["gpu_launches"] >= 2 * d["steps"] and d["clocks"]["reasons"] == []
+    assert d["value"] / c["value"] > 1e5                     # GPU arm vs the reference's Python loop on the host cores
