@@ -204,3 +204,28 @@ def test_committed_bench_line_carries_the_contract_keys():
     assert set(("value", "unit", "cores", "kind", "sample")) <= set(c) and c["kind"] in ("reference", "port")
     assert d["gpu_launches"] >= 2 * d["steps"] and d["clocks"]["reasons"] == []
     assert d["value"] / c["value"] > 1e5                     # GPU arm vs the reference's Python loop on the host cores
+
+
+def test_shared_initial_state_bookkeeping_without_a_device():
+    """y0 given as ONE row marks the ensemble as a pure parameter sweep (problem.y0_row, solver._y_row): the host never
+    builds an ensemble-sized initial-state array after construction, and re_init / reset keep or drop the mark."""
+    mu = np.linspace(0.1, 10.0, 50)[:, None]
+    prob = Batched_Explicit_Problem(model="vdp", y0=[2.0, -0.6], p0=mu)
+    assert prob.N == 50 and prob.y0.shape == (50, 2) and np.array_equal(prob.y0_row, [2.0, -0.6])
+    assert Batched_Explicit_Problem(model="vdp", y0=np.tile([2.0, -0.6], (50, 1)), p0=mu).y0_row is None
+    assert Batched_Explicit_Problem(model="vdp", y0=[2.0, -0.6]).y0_row is None          # a single member is just a member
+    sim = Dopri5(prob)
+    assert np.array_equal(sim._y_row, [2.0, -0.6]) and sim.y.shape == (50, 2)
+    sim.re_init(0.5, [1.0, 0.0])
+    assert sim.t == 0.5 and np.array_equal(sim._y_row, [1.0, 0.0])
+    assert sim.y.shape == (50, 2) and sim.y.strides[0] == 0 and (sim.y == [1.0, 0.0]).all()   # a view, not N rows
+    sim.re_init(0.0, np.arange(100.0).reshape(50, 2))
+    assert sim._y_row is None and sim.y[7, 1] == 15.0
+    sim.reset()
+    assert np.array_equal(sim._y_row, [2.0, -0.6]) and sim.t == 0.0 and sim._dirty
+    with pytest.raises(Explicit_ODE_Exception):
+        sim.re_init(0.0, np.zeros((49, 2)))
+    with pytest.raises(Explicit_ODE_Exception):
+        sim.re_init(0.0, [1.0, 2.0, 3.0])
+    sim.reduce_rows = 1
+    assert sim.reduce_rows is True and sim.get_options()["reduce_rows"] is True
