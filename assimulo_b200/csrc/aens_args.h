@@ -58,6 +58,12 @@ typedef struct {
     int zc;                   /* 1: zero-copy mode (the in_* / out_* pointers above are in use) */
     int y0_shared;            /* zero-copy mode: every member starts from y0_row instead of a row of in_y */
     double y0_row[AENS_MAX_N];
+    /* time limit of this simulate() call in nanoseconds of %globaltimer, 0 = none (ODE.time_limit, src/ode.pyx:372-392;
+     * checked in Explicit_ODE.report_solution, src/explicit_ode.pyx:290-292).  *t_start holds the call's start time
+     * (written by the first warp that fetches work); a warp that fetches members after the deadline stores them
+     * unintegrated with status AENS_ST_TIME_LIMIT. */
+    unsigned long long limit_ns;
+    unsigned long long *t_start; /* start time of the simulate() call, shared by all launches of a chunked call */
 } aens_args_t;
 
 #endif

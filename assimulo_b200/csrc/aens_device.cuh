@@ -334,14 +334,27 @@ AENS_DEV int *aens_red_lock() {
     return lock;
 }
 
+template <int ITEMS, int RS>
+struct RedShared {
+    double tile[AENS_BLOCK / 32][ITEMS][33];
+    unsigned tmask[AENS_BLOCK / 32][RS];
+};
+template <int ITEMS, int RS>
+AENS_DEV RedShared<ITEMS, RS> &aens_red_shared() {
+    __shared__ RedShared<ITEMS, RS> sh;
+    return sh;
+}
+
 template <class M, class S>
 AENS_DEV void aens_reduce_grid(S &s, Lane<M> &L, const aens_args_t &a, double t) {
     constexpr int N = M::N, REC = 5 * N + 1;
     /* rows handled per pass: a step usually crosses several rows, and up to 32 (row, component) items give every
      * lane of the warp one column to accumulate in the loop below; 33-double pitch = conflict-free both ways */
     constexpr int RS = (32 / N) > 8 ? 8 : (32 / N), ITEMS = RS * N;
-    __shared__ double tile[AENS_BLOCK / 32][ITEMS][33];
-    __shared__ unsigned tmask[AENS_BLOCK / 32][RS];
+    /* (one shared tile per kernel whatever the interpolant type: see aens_red_shared) */
+    RedShared<ITEMS, RS> &sh = aens_red_shared<ITEMS, RS>();
+    double (*tile)[ITEMS][33] = sh.tile;
+    unsigned (*tmask)[RS] = sh.tmask;
     const unsigned lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
     const unsigned mask = __activemask();
     bool pend = L.gi < a.n_grid && __ldg(a.t_grid + L.gi) <= t;
@@ -467,6 +480,26 @@ AENS_DEV void aens_emit_grid(S &s, Lane<M> &L, const aens_args_t &a, long long i
 #pragma unroll
         for (int i = 0; i < M::N; ++i) a.dense[((long long)L.gi * M::N + i) * a.N + idx] = out[i];
         L.gi += 1;
+    }
+}
+
+/* Grid rows at or before the start of a segment (the first SOLOUT call of dopri5 / radau5 / rodas with XOLD = X reports
+ * them from the state itself, dopri5.f:399-404): the same emit path as every other row -- stored by the d1 kernels,
+ * reduced over the ensemble by the d2 kernels (which have no row buffer at all). */
+template <class M, bool RED>
+struct HoldState {
+    static constexpr bool REDUCE = RED;
+    const double *y;
+    AENS_DEV void interp(double, double *out) const {
+#pragma unroll
+        for (int i = 0; i < M::N; ++i) out[i] = y[i];
+    }
+};
+template <class M, class S>
+AENS_DEV void aens_emit_start(Lane<M> &L, const aens_args_t &a, long long idx) {
+    if (L.gi < a.n_grid && __ldg(a.t_grid + L.gi) <= L.t) {
+        HoldState<M, S::REDUCE> hs{L.y};
+        aens_emit_grid<M, HoldState<M, S::REDUCE> >(hs, L, a, idx, L.t);
     }
 }
 
@@ -1052,13 +1085,7 @@ struct Dopri5 {
         /* first SOLOUT call (XOLD = X, dopri5.f:399-404): Assimulo runs the locator on a zero-length interval --
          * one more g evaluation at the very same point, never an event -- and reports grid rows <= t */
         if (M::NG > 0) L.st[AENS_STAT_NSTATEFCNS] += 1;
-        if (DENSE) {
-            while (L.gi < a.n_grid && __ldg(a.t_grid + L.gi) <= L.t) {
-#pragma unroll
-                for (int i = 0; i < N; ++i) a.dense[((long long)L.gi * N + i) * a.N + idx] = L.y[i];
-                L.gi += 1;
-            }
-        }
+        if (DENSE) aens_emit_start<M, Dopri5>(L, a, idx);
     }
 
     AENS_DEV int attempt(const aens_args_t &a, long long idx) {
@@ -1385,8 +1412,19 @@ __device__ __forceinline__ void aens_run(const aens_args_t &a) {
             const int nidle = __popc(idle_mask);
             const int leader = __ffs(idle_mask) - 1;
             unsigned long long base = 0;
-            if (lane == leader) base = atomicAdd(a.queue, (unsigned long long)nidle);
+            int late = 0; /* warp-uniform: this batch is fetched after the call's time limit */
+            if (lane == leader) {
+                base = atomicAdd(a.queue, (unsigned long long)nidle);
+                if (a.limit_ns) { /* ODE.time_limit: checked when a warp asks for work, i.e. between members */
+                    unsigned long long now;
+                    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+                    unsigned long long t_start = atomicCAS(a.t_start, 0ull, now);
+                    if (t_start == 0ull) t_start = now;
+                    late = (now - t_start > a.limit_ns) ? 1 : 0;
+                }
+            }
             base = __shfl_sync(FULL, base, leader);
+            late = __shfl_sync(FULL, late, leader);
             if (phase == PH_IDLE) {
                 /* results leave the registers here, for all idle lanes of the warp at once: lanes that were fetched
                  * together hold consecutive members, so their rows form contiguous blocks (SoA state in HBM and, in
@@ -1412,8 +1450,16 @@ __device__ __forceinline__ void aens_run(const aens_args_t &a) {
                     s.L.load(a, idx);
                     s.load_aux(a, idx);
                     /* driver loop test, explicit_ode.pyx:209 */
-                    if (s.L.t + eps * aens::dmax(aens::dabs(s.L.t), aens::dabs(a.tf)) < a.tf) phase = PH_SEGINIT;
-                    else pending = true;
+                    if (s.L.t + eps * aens::dmax(aens::dabs(s.L.t), aens::dabs(a.tf)) < a.tf) {
+                        if (late) { /* TimeLimitExceeded (explicit_ode.pyx:290-292): stored as fetched, not integrated */
+                            s.L.status = AENS_ST_TIME_LIMIT;
+                            pending = true;
+                        } else {
+                            phase = PH_SEGINIT;
+                        }
+                    } else {
+                        pending = true;
+                    }
                 }
             }
             if (a.q_begin + (long long)base + nidle >= a.q_end) drained = true;

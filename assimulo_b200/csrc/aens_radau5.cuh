@@ -376,11 +376,7 @@ struct Radau5 {
         theta = 0.;
         st = S_JAC;
         /* grid rows at the segment start (see Dopri5::seg_init) */
-        while (L.gi < a.n_grid && __ldg(a.t_grid + L.gi) <= L.t) {
-#pragma unroll(N <= 4 ? 64 : 1)
-            for (int i = 0; i < N; ++i) a.dense[((long long)L.gi * N + i) * a.N + idx] = L.y[i];
-            L.gi += 1;
-        }
+        aens_emit_start<M, Radau5>(L, a, idx);
     }
 
     /* after an unexpected rejection / singular matrix (labels L78 and the tail shared with rejections) */
@@ -752,11 +748,7 @@ struct Rodas {
         hacc = 0.0; erracc = 0.0;
         /* first SOLOUT (rodas_decsol.f:582-589): one g evaluation on a zero-length interval, rows <= x */
         if (M::NG > 0) L.st[AENS_STAT_NSTATEFCNS] += 1;
-        while (L.gi < a.n_grid && __ldg(a.t_grid + L.gi) <= L.t) {
-#pragma unroll(N <= 4 ? 64 : 1)
-            for (int i = 0; i < N; ++i) a.dense[((long long)L.gi * N + i) * a.N + idx] = L.y[i];
-            L.gi += 1;
-        }
+        aens_emit_start<M, Rodas>(L, a, idx);
     }
 
     AENS_DEV int attempt(const aens_args_t &a, long long idx) {

@@ -84,10 +84,23 @@ cdef extern from "assimulo_cuda.h":
     int aens_set_row_reduction(aens_handle_t *h, int on) nogil
     int aens_get_row_reduction(aens_handle_t *h, double *mean, double *var, double *mn, double *mx,
                                long long *count) nogil
+    int aens_set_time_limit(aens_handle_t *h, double seconds) nogil
+    int aens_comm_unique_id(void *id128) nogil
+    int aens_comm_init(aens_handle_t *h, int rank, int nranks, const void *id128) nogil
+    int aens_comm_destroy(aens_handle_t *h) nogil
+    int aens_allgather_results(aens_handle_t *h, int what) nogil
+    int aens_last_gather_ms(aens_handle_t *h, float *ms) nogil
+    int aens_gathered_ptr(aens_handle_t *h, void **ptr, long long *rec_bytes, int *nranks) nogil
+    int aens_get_gathered(aens_handle_t *h, long long n_total, double *t, double *y, int *status, int *stats,
+                          double *ev_t, int *ev_info) nogil
+    int aens_measure_hostlink(int device, long long nbytes, int mode, double seconds, double *gbs) nogil
 
 STAT_NAMES = ("nsteps", "nfcns", "nerrfails", "njacs", "nlus", "nstatefcns", "nstateevents", "nstepstotal",
               "ntimeevents", "nniters", "nnfails")
 MODEL_HAS_JAC, MODEL_TIME_EVENTS, MODEL_RHS_H = 1, 2, 4
+GATHER_T, GATHER_Y, GATHER_STATUS, GATHER_STATS, GATHER_EVENTS = 1, 2, 4, 8, 16
+HOSTLINK_MODES = ("copy engine H2D", "copy engine D2H", "copy engine H2D+D2H", "SM reads of host memory",
+                  "SM writes to host memory", "SM reads+writes")
 SOLVER_IDS = {"ExplicitEuler": 0, "RungeKutta4": 1, "RungeKutta34": 2, "Dopri5": 3, "Radau5ODE": 4,
               "ImplicitEuler": 5, "RodasODE": 6}
 MAX_N = 16
@@ -168,6 +181,32 @@ def pinned_empty(shape, dtype=np.float64):
     cdef np.ndarray raw = np.PyArray_SimpleNewFromData(1, &n, np.NPY_UINT8, blk.ptr)
     np.set_array_base(raw, blk)
     return raw.view(dt).reshape(shape)
+
+
+def comm_unique_id():
+    """128-byte NCCL id for aens_comm_init: rank 0 creates it, the host program hands it to the other ranks."""
+    cdef char buf[128]
+    cdef int rc = aens_comm_unique_id(buf)
+    if rc != 0:
+        raise AensError(rc, "aens_comm_unique_id failed (libnccl.so.2 not loadable?)")
+    return bytes(buf[:128])
+
+
+def measure_hostlink(int device=0, long long nbytes=1 << 28, int mode=0, double seconds=0.25):
+    """GB/s the host link of `device` sustains in `mode` (index into HOSTLINK_MODES)."""
+    cdef double gbs = 0.0
+    cdef int rc
+    with nogil:
+        rc = aens_measure_hostlink(device, nbytes, mode, seconds, &gbs)
+    if rc != 0:
+        raise AensError(rc, "host link measurement failed (no GPU?)")
+    return gbs
+
+
+cdef _need(np.ndarray a, dtype, long long size, name):
+    """explicit argument checks (an `assert` disappears under python -O and a short buffer is a host memory overrun)"""
+    if a.dtype != dtype or a.size != size or not a.flags.c_contiguous:
+        raise ValueError("%s must be a C-contiguous %s array with %d elements" % (name, np.dtype(dtype).name, size))
 
 
 def measure_fp64_peak(int device=0, double seconds=1.0):
@@ -326,7 +365,7 @@ cdef class Handle:
         cdef const int *op = NULL
         if order is not None:
             od = np.ascontiguousarray(order, dtype=np.intc)
-            if od.shape[0] != self.N:
+            if od.shape[0] != self.N or not np.array_equal(np.sort(od), np.arange(self.N, dtype=np.intc)):
                 raise ValueError("order must be a permutation of range(N)")
             op = &od[0]
         cdef int rc
@@ -340,8 +379,96 @@ cdef class Handle:
             rc = aens_simulate(self.h, tfinal)
         self._check(rc)
 
+    def set_time_limit(self, double seconds):
+        """ODE.time_limit: members a warp fetches later than `seconds` after the launch started are not integrated
+        (status -9); 0 = no limit."""
+        self._check(aens_set_time_limit(self.h, seconds))
+
+    # ---- the final all-gather over NCCL (SURVEY 8e) ----
+    def comm_init(self, int rank, int nranks, bytes uid):
+        if len(uid) != 128:
+            raise ValueError("the communicator id is 128 bytes (comm_unique_id)")
+        cdef const char *p = uid
+        cdef int rc
+        with nogil:
+            rc = aens_comm_init(self.h, rank, nranks, p)
+        self._check(rc)
+
+    def comm_destroy(self):
+        self._check(aens_comm_destroy(self.h))
+
+    def allgather_results(self, int what=0):
+        """ONE ncclAllGather of this rank's packed results (asynchronous on the handle's stream)."""
+        cdef int rc
+        with nogil:
+            rc = aens_allgather_results(self.h, what)
+        self._check(rc)
+
+    def last_gather_ms(self):
+        cdef float ms = 0
+        cdef int rc
+        with nogil:
+            rc = aens_last_gather_ms(self.h, &ms)
+        self._check(rc)
+        return ms
+
+    def gathered_ptr(self):
+        cdef void *p = NULL
+        cdef long long b = 0
+        cdef int r = 0
+        self._check(aens_gathered_ptr(self.h, &p, &b, &r))
+        return <size_t>p, b, r
+
+    def get_gathered(self, long long n_total, bint want_t=True, bint want_y=True, bint want_status=True,
+                     bint want_stats=True, bint want_events=False):
+        """The gathered results of the first n_total members (rank order) as host arrays: dict with t[N], y[N, n],
+        status[N], stats[11, N] and, for models with events, ev_t / ev_info [N, slots]."""
+        cdef np.ndarray[double, ndim=1, mode="c"] t
+        cdef np.ndarray[double, ndim=2, mode="c"] y
+        cdef np.ndarray[int, ndim=1, mode="c"] st
+        cdef np.ndarray[int, ndim=2, mode="c"] stats
+        cdef np.ndarray[double, ndim=2, mode="c"] evt
+        cdef np.ndarray[int, ndim=2, mode="c"] evi
+        cdef double *tp = NULL
+        cdef double *yp = NULL
+        cdef int *sp = NULL
+        cdef int *ssp = NULL
+        cdef double *etp = NULL
+        cdef int *eip = NULL
+        out = {}
+        if want_t:
+            t = np.empty(n_total, dtype=np.float64)
+            tp = &t[0]
+            out["t"] = t
+        if want_y:
+            y = np.empty((n_total, self.n), dtype=np.float64)
+            yp = &y[0, 0]
+            out["y"] = y
+        if want_status:
+            st = np.empty(n_total, dtype=np.intc)
+            sp = &st[0]
+            out["status"] = st
+        if want_stats:
+            stats = np.empty((len(STAT_NAMES), n_total), dtype=np.intc)
+            ssp = &stats[0, 0]
+            out["stats"] = stats
+        cdef int S = self.event_slots if ((self.n_g > 0 or (self.has_jac & 2)) and self.event_slots > 0) else 0
+        if want_events and S > 0:
+            evt = np.empty((n_total, S), dtype=np.float64)
+            evi = np.empty((n_total, S), dtype=np.intc)
+            etp = &evt[0, 0]
+            eip = &evi[0, 0]
+            out["ev_t"] = evt
+            out["ev_info"] = evi
+        cdef int rc
+        with nogil:
+            rc = aens_get_gathered(self.h, n_total, tp, yp, sp, ssp, etp, eip)
+        self._check(rc)
+        return out
+
     def set_host_mode(self, int mode):
-        """0 auto, 1 chunked staging pipeline, 2 zero-copy (raises at simulate_host if the arrays are not mappable)."""
+        """0 auto, 1 chunked staging pipeline (copy engines both ways), 2 zero-copy (raises at simulate_host if the
+        arrays are not mappable), 3 chunked with zero-copy inputs and copy-engine results, 4 the other way round."""
         self._check(aens_set_host_mode(self.h, mode))
 
     def set_fetch_reverse(self, int reverse):
@@ -380,19 +507,19 @@ cdef class Handle:
         cdef np.ndarray a
         if out_y is not None:
             a = out_y
-            assert a.dtype == np.float64 and a.size == N * self.n and a.flags.c_contiguous
+            _need(a, np.float64, N * self.n, "out_y")
             yo = <double*>np.PyArray_DATA(a)
         if out_t is not None:
             a = out_t
-            assert a.dtype == np.float64 and a.size == N and a.flags.c_contiguous
+            _need(a, np.float64, N, "out_t")
             to = <double*>np.PyArray_DATA(a)
         if out_sw is not None and self.n_sw:
             a = out_sw
-            assert a.dtype == np.uint8 and a.size == N * self.n_sw and a.flags.c_contiguous
+            _need(a, np.uint8, N * self.n_sw, "out_sw")
             so = <unsigned char*>np.PyArray_DATA(a)
         if out_status is not None:
             a = out_status
-            assert a.dtype == np.intc and a.size == N and a.flags.c_contiguous
+            _need(a, np.intc, N, "out_status")
             sto = <int*>np.PyArray_DATA(a)
         cdef const double *yptr = &y[0, 0]
         cdef long long sums[11]
@@ -500,15 +627,15 @@ cdef class Handle:
         cdef object so = None
         if want_t:
             t_arr = out_t if out_t is not None else np.empty(self.N, dtype=np.float64)
-            assert t_arr.dtype == np.float64 and t_arr.size == self.N and t_arr.flags.c_contiguous
+            _need(t_arr, np.float64, self.N, "out_t")
             tp = <double*>np.PyArray_DATA(t_arr)
             to = t_arr
         st_arr = out_status if out_status is not None else np.empty(self.N, dtype=np.intc)
-        assert st_arr.dtype == np.intc and st_arr.size == self.N and st_arr.flags.c_contiguous
+        _need(st_arr, np.intc, self.N, "out_status")
         stp = <int*>np.PyArray_DATA(st_arr)
         if want_y:
             y_arr = out_y if out_y is not None else np.empty((self.N, self.n), dtype=np.float64)
-            assert y_arr.dtype == np.float64 and y_arr.size == self.N * self.n and y_arr.flags.c_contiguous
+            _need(y_arr, np.float64, self.N * self.n, "out_y")
             yp = <double*>np.PyArray_DATA(y_arr)
             yo = y_arr
         if want_sw and self.n_sw:

@@ -19,7 +19,8 @@ for _name, _doc in (
         ("Radau_Exception", "Radau5ODE option validation"),
         ("Rodas_Exception", "RodasODE option validation"),
         ("TerminateSimulation", "what handle_event raises in the reference to stop a run; per-member status 1 here"),
-        ("TimeLimitExceeded", "the reference's time_limit abort; the batched solvers accept the option but never raise it"),
+        ("TimeLimitExceeded", "the reference's time_limit abort (src/explicit_ode.pyx:290-292): raised by simulate() when members "
+         "were still waiting for a warp at the deadline; their status is -9, everything else is kept"),
 ):
     _named(_name, _doc)
 del _name, _doc

@@ -40,10 +40,12 @@ class Batched_Explicit_Problem(object):
         sw0     [N, n_sw] switches (Explicit_Problem.sw0)
         t0      common start time
         N       ensemble size, only needed when neither y0 nor p0 is 2-D
+        detect_shared_y0  notice [N, n] initial states whose rows are all equal (default): the solvers then send
+                one row to the device instead of N
     """
 
     def __init__(self, model=None, y0=None, p0=None, sw0=None, t0=0.0, name="---", source=None, n=None, n_p=0,
-                 n_g=0, n_sw=0, has_jac=False, N=None, time_events=False, fused_rhs=False):
+                 n_g=0, n_sw=0, has_jac=False, N=None, time_events=False, fused_rhs=False, detect_shared_y0=True):
         if (model is None) == (source is None):
             raise AssimuloException("Give exactly one of model= (built-in) or source= (CUDA C string).")
         if model is not None:
@@ -80,6 +82,11 @@ class Batched_Explicit_Problem(object):
         #: the one initial state all members share, when y0 was given as a single row (a pure parameter sweep): the
         #: solvers then pass this row instead of [N, n] to the device (aens_set_shared_y0)
         self.y0_row = y0.reshape(-1).copy() if (y0.size == self.n and N > 1) else None
+        if detect_shared_y0 and self.y0_row is None and y0.ndim == 2 and N > 1 and y0.shape[0] == N and \
+                (y0 == y0[0]).all():
+            # the same sweep written the long way (N identical rows, as a loop over Explicit_Problem(rhs_i, y0) holds
+            # them): detected once here so that the solvers still send ONE row instead of [N, n] per simulate()
+            self.y0_row = y0[0].copy()
         self.y0 = np.ascontiguousarray(np.broadcast_to(y0.reshape(-1, self.n) if y0.ndim == 2 else y0[None, :],
                                                        (N, self.n)))
         if self.n_p:

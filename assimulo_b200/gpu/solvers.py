@@ -20,7 +20,7 @@ There is no CPU fallback: creating the device handle raises if no CUDA device is
 import numpy as np
 
 from .exception import (AssimuloException, Dopri5_Exception, Explicit_ODE_Exception, Radau_Exception,
-                        Rodas_Exception)
+                        Rodas_Exception, TimeLimitExceeded)
 from .problem import Batched_Explicit_Problem
 
 ARITH = {"strict": 0, "fast": 1}
@@ -28,7 +28,9 @@ STAT_NAMES = ("nsteps", "nfcns", "nerrfails", "njacs", "nlus", "nstatefcns", "ns
               "ntimeevents", "nniters", "nnfails")
 
 # status codes (include/assimulo_cuda.h)
-ST_COMPLETE, ST_TERMINATED = 0, 1
+ST_COMPLETE, ST_TERMINATED, ST_TIME_LIMIT = 0, 1, -9
+#: how simulate() moves host arrays when it takes the one-call host path (aens_set_host_mode)
+HOST_MODES = {"auto": 0, "staged": 1, "zero-copy": 2, "zero-copy-in": 3, "zero-copy-out": 4}
 
 
 def _core():
@@ -65,7 +67,7 @@ class Batched_Explicit_ODE(object):
         self.options = {"report_continuously": False, "display_progress": True, "verbosity": 30, "backward": False,
                         "store_event_points": True, "time_limit": 0, "clock_step": False, "num_threads": 1,
                         "arith": "fast", "refill_threshold": 32, "order": None, "event_slots": 16,
-                        "reuse_buffers": False, "host_chunks": None, "reduce_rows": False}
+                        "reuse_buffers": False, "host_chunks": None, "reduce_rows": False, "host_mode": "auto"}
         self.supports = {"state_events": False, "interpolated_output": False, "report_continuously": False}
         self.problem_info = {"dim": problem.n, "dimRoot": problem.n_g, "state_events": problem.n_g > 0,
                              "jac_fcn": problem.has_jac, "switches": problem.n_sw > 0}
@@ -198,6 +200,8 @@ class Batched_Explicit_ODE(object):
             order = None
         h.set_fetch_reverse(reverse)
         h.set_opts(self._opts_dict())
+        h.set_time_limit(float(self.options["time_limit"] or 0.0))
+        h.set_host_mode(HOST_MODES[self.options["host_mode"]])
         pin = None
         if self.options["reuse_buffers"]:
             # page-locked result buffers allocated once and overwritten by every simulate() call: rows returned
@@ -273,6 +277,12 @@ class Batched_Explicit_ODE(object):
         self.t = tfinal if nbad == 0 else float(np.min(self.t_members))
         self.finalize()
         self.problem.finalize(self)
+        if nbad and self.options["time_limit"] and (self.status == ST_TIME_LIMIT).any():
+            # the reference raises from report_solution in the middle of the run (src/explicit_ode.pyx:290-292); here
+            # every member that was started has finished and its result is kept (self.y, self.status, statistics)
+            late = int((self.status == ST_TIME_LIMIT).sum())
+            raise TimeLimitExceeded("The time limit was exceeded at integration time %.8E (%d of %d members not "
+                                    "integrated)." % (self.t, late, self.N))
         if self.options["reuse_buffers"]:
             return self.t_sol, self.y_sol  # list of [N, n] rows, no ensemble-sized stacking copy
         return self.t_sol, np.array(self.y_sol)
@@ -360,8 +370,9 @@ class Batched_Explicit_ODE(object):
             raise AssimuloException("The time limit must be positive or zero.")
         self.options["time_limit"] = time_limit
     time_limit = property(lambda self: self.options["time_limit"], _set_time_limit,
-                          doc="Accepted for compatibility; one launch integrates the whole ensemble, there is no "
-                              "per-step host loop to interrupt (src/ode.pyx:372-392).")
+                          doc="Upper bound in seconds for one simulate() call, 0 = none (src/ode.pyx:372-392).  The "
+                              "device checks it whenever a warp asks for its next members: members not started by "
+                              "then keep their state (status -9) and simulate() raises TimeLimitExceeded.")
 
     def _set_display_progress(self, v):
         self.options["display_progress"] = bool(v)
@@ -435,6 +446,15 @@ class Batched_Explicit_ODE(object):
     def _set_event_slots(self, v):
         self.options["event_slots"] = int(v)
     event_slots = property(_get_event_slots, _set_event_slots)
+
+    def _set_host_mode(self, v):
+        if v not in HOST_MODES:
+            raise AssimuloException("host_mode must be one of %s." % sorted(HOST_MODES))
+        self.options["host_mode"] = v
+    host_mode = property(lambda self: self.options["host_mode"], _set_host_mode,
+                         doc="How simulate() moves host arrays when inputs and results live in host memory: 'auto' / "
+                             "'zero-copy' (one launch, the warps read and write page-locked host memory themselves), "
+                             "'staged' (chunked copy-engine pipeline), 'zero-copy-in' / 'zero-copy-out' (one side each).")
 
     def _get_reduce_rows(self):
         """True: the rows of the output grid (ncp / ncp_list) are reduced over the ensemble inside the integration

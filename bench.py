@@ -228,76 +228,171 @@ def workload_config(a, n_total):
                                    % (a.members * (3 + 3 + 1.5 + 4) * 8 / 1e6),
             "fetch": "descending member index (cost grows with mu), 32-member batches per warp",
             "parallelism": "members sharded over %d GPU(s), 32-member chunks dealt round-robin, no data-path "
-                           "collective; one all_gather of final states at the end (not in the timed region)" % a.gpus}
+                           "collective; ONE ncclAllGather of {t, y, status} at the end of every e2e step" % a.gpus}
 
 
 # ------------------------------------------------------------------------------------------------------
-# the other BASELINE.json configurations (N = 1 only; reported in the same JSON line under "configs")
+# the other BASELINE.json configurations: in the headline line under "configs" (N = 1), or one at a time at any
+# number of GPUs with --config NAME (weak scaling, members dealt like the headline's)
 # ------------------------------------------------------------------------------------------------------
-def run_other_configs(device, peak_tflops, hbm_gbs):
-    """cfg 2-5 of BASELINE.json at full size, inputs resident in HBM, best of 3 kernel launches each (CUDA events
-    on the launching stream).  flops/step follow DESIGN.md section 3."""
+def deal(n_total, rank, world, per_rank):
+    """global member indices of this rank: 32-member chunks of the global sweep dealt round-robin"""
+    chunks = np.arange(rank, n_total // 32, world)[: per_rank // 32]
+    return (chunks[:, None] * 32 + np.arange(32)[None, :]).reshape(-1)
+
+
+def config_table():
+    """name -> dict(members per GPU, model, solver, builder(n_total, idx) -> (y0, p, sw0), tf, flops per accepted
+    step, options).  Flop counts follow the SURVEY 8(d) convention; Radau5ODE's is the
+    instrumented count of the CPU oracle on this very ensemble (oracle/ens_oracle.c, AENS_ORACLE_FLOPS)."""
     import cases
+    grid100 = np.linspace(0.0, 0.1, 101)[1:]
+    rob_opts = dict(rtol=1e-6, atol=np.array(cases.ROBERTSON_ATOL), usejac=1)
+    gyro_flops = 81 * 12 + 6 * 39 + 20
+    return {
+        "cfg2_rk4": dict(title="cfg2 RungeKutta4 h=1e-3 (strict arithmetic, bit-exact vs reference)", members=1 << 20,
+                         model="vdp", solver="RungeKutta4", build=cases.vdp_sweep, tf=2.0, flops=15 * 2 + 4 * 5 + 7,
+                         opts=dict(h=1e-3), reverse=True),
+        "cfg2_rk34": dict(title="cfg2 RungeKutta34 rtol=atol=1e-6", members=1 << 20, model="vdp", solver="RungeKutta34",
+                          build=cases.vdp_sweep, tf=2.0, flops=30 * 2 + 5 * 5 + 12,
+                          opts=dict(rtol=1e-6, atol=1e-6, inith=0.01), reverse=True),
+        "cfg3": dict(title="cfg3 Dopri5 bouncing ball, state events on device", members=1 << 20, model="ball",
+                     solver="Dopri5", build=cases.ball_sweep, tf=3.0, flops=81 * 2 + 20, opts=dict(rtol=1e-6, atol=1e-6)),
+        "cfg4": dict(title="cfg4 Radau5ODE Robertson, analytic Jacobian", members=1 << 18, model="robertson",
+                     solver="Radau5ODE", build=cases.robertson_sweep, tf=40.0, flops=RADAU_ROBERTSON_FLOPS, opts=rob_opts),
+        "cfg4_rodas": dict(title="cfg4' RodasODE Robertson, analytic Jacobian", members=1 << 18, model="robertson",
+                           solver="RodasODE", build=cases.robertson_sweep, tf=40.0, flops=420, opts=rob_opts),
+        "cfg5": dict(title="cfg5 Dopri5 gyro (12 states), dense output every 1e-3", members=1 << 22, model="gyro",
+                     solver="Dopri5", build=cases.gyro_sweep, tf=0.1, flops=gyro_flops, t_grid=grid100,
+                     opts=dict(rtol=1e-8, atol=1e-8)),
+        "cfg5_reduced": dict(title="cfg5' the same with the 100 rows reduced over the ensemble in the kernel "
+                                   "(mean/var/min/max, no dense buffer)", members=1 << 22, model="gyro", solver="Dopri5",
+                             build=cases.gyro_sweep, tf=0.1, flops=gyro_flops, t_grid=grid100, reduce_rows=True,
+                             opts=dict(rtol=1e-8, atol=1e-8)),
+    }
+
+
+# Radau5ODE on the cfg4 Robertson ensemble: fp64 flops per ACCEPTED step counted by the instrumented CPU oracle over
+# every 64th member (tools/radau_flops.py; SURVEY 8(d) asked for a count instead of the 1040 estimate of round 1)
+RADAU_ROBERTSON_FLOPS = 1040
+try:
+    RADAU_ROBERTSON_FLOPS = float(json.load(open(os.path.join(ROOT, "profiles", "r2_radau_flops.json")))["flops_per_accepted_step"])
+except Exception:
+    pass
+
+
+def run_config(device, cfg, rank, world, peak_tflops, hbm_gbs, steps=3, warmup=1):
+    """One configuration on this rank's GPU, inputs resident in HBM: `warmup` untimed passes, then `steps` passes of
+    (reset + kernel) timed with CUDA events on the launching stream.  Returns the per-rank record."""
     from assimulo_b200.gpu import _core
-    out = []
+    per = cfg["members"]
+    n_total = per * world
+    idx = deal(n_total, rank, world, per) if world > 1 else None
+    arrs = cfg["build"](n_total, idx)
+    y0, p = arrs[0], arrs[1]
+    sw0 = arrs[2] if len(arrs) > 2 else None
+    h = _core.Handle(device)
+    h.set_model_builtin(cfg["model"])
+    h.set_ensemble(y0, p, sw0, 0.0)
+    d = {"solver": _core.SOLVER_IDS[cfg["solver"]]}
+    d.update(cfg["opts"])
+    h.set_opts(d)
+    h.set_row_reduction(bool(cfg.get("reduce_rows")))
+    h.set_output(cfg.get("t_grid"), 16)
+    h.set_fetch_reverse(bool(cfg.get("reverse")))
+    for _ in range(warmup):
+        h.reset()
+        h.simulate(cfg["tf"])
+    l0 = h.launch_count()
+    for _ in range(steps):
+        h.reset()
+        h.simulate_async(cfg["tf"])
+    h.sync()
+    launches = h.launch_count() - l0
+    ms_all = h.kernel_ms_history(steps)
+    ms = float(np.mean(ms_all))
+    sums, nbad = h.get_summary()
+    n = y0.shape[1]
+    flops = cfg["flops"]
+    rec = {"name": cfg["title"], "members": int(y0.shape[0]), "model": cfg["model"], "solver": cfg["solver"],
+           "kernel_ms": ms, "stat": "mean of %d launches after %d warm-up" % (steps, warmup),
+           "kernel_ms_min": float(min(ms_all)), "accepted_steps": int(sums["nsteps"]),
+           "value": sums["nsteps"] / (ms * 1e-3), "unit": UNIT,
+           "not_complete": int(nbad), "state_events": int(sums["nstateevents"]), "state_event_probes": int(sums["nstatefcns"]),
+           "flops_per_accepted_step": flops, "gpu_launches": int(launches),
+           "fp64_frac": sums["nsteps"] * flops / (ms * 1e-3) / 1e12 / peak_tflops}
+    if cfg.get("reduce_rows"):   # the rows never reach HBM: [rows, n] statistics come back instead of [rows, N, n]
+        rs = h.get_row_reduction()
+        rec["rows_reduced_in_kernel"] = int(len(cfg["t_grid"]))
+        rec["members_in_last_row"] = int(rs["count"][-1])
+    elif cfg.get("t_grid") is not None:
+        nbytes = float(len(cfg["t_grid"])) * n * 8 * y0.shape[0]
+        rec["dense_bytes"] = nbytes
+        rec["hbm_write_frac"] = nbytes / (ms * 1e-3) / 1e9 / hbm_gbs
+    h.close()
+    return rec
 
-    def run(name, model, solver, y0, p, sw0, tf, flops, t_grid=None, reverse=False, reduce_rows=False, **opts):
-        h = _core.Handle(device)
-        h.set_model_builtin(model)
-        h.set_ensemble(y0, p, sw0, 0.0)
-        d = {"solver": _core.SOLVER_IDS[solver]}
-        d.update(opts)
-        h.set_opts(d)
-        h.set_row_reduction(reduce_rows)
-        h.set_output(t_grid, 16)
-        h.set_fetch_reverse(reverse)
-        ms = []
-        for _ in range(4):
-            h.reset()
-            h.simulate(tf)
-            ms.append(h.last_kernel_ms())
-        ms = min(ms[1:])
-        sums, nbad = h.get_summary()
-        n = y0.shape[1]
-        rec = {"name": name, "members": int(y0.shape[0]), "model": model, "solver": solver, "kernel_ms": ms,
-               "accepted_steps": int(sums["nsteps"]), "value": sums["nsteps"] / (ms * 1e-3), "unit": UNIT,
-               "not_complete": int(nbad), "state_events": int(sums["nstateevents"]),
-               "flops_per_accepted_step": flops,
-               "fp64_frac": sums["nsteps"] * flops / (ms * 1e-3) / 1e12 / peak_tflops}
-        if reduce_rows:   # the rows never reach HBM: [rows, n] statistics come back instead of [rows, N, n]
-            rs = h.get_row_reduction()
-            rec["rows_reduced_in_kernel"] = int(len(t_grid))
-            rec["members_in_last_row"] = int(rs["count"][-1])
-        elif t_grid is not None:
-            nbytes = float(len(t_grid)) * n * 8 * y0.shape[0]
-            rec["dense_bytes"] = nbytes
-            rec["hbm_write_frac"] = nbytes / (ms * 1e-3) / 1e9 / hbm_gbs
-        h.close()
-        out.append(rec)
 
-    N = 1 << 20
-    y0, mu = cases.vdp_sweep(N)
-    run("cfg2 RungeKutta4 h=1e-3 (strict arithmetic, bit-exact vs reference)", "vdp", "RungeKutta4", y0, mu, None, 2.0,
-        15 * 2 + 4 * 5 + 7, h=1e-3, reverse=True)
-    run("cfg2 RungeKutta34 rtol=atol=1e-6", "vdp", "RungeKutta34", y0, mu, None, 2.0, 30 * 2 + 5 * 5 + 12,
-        rtol=1e-6, atol=1e-6, inith=0.01, reverse=True)
-    y0, p, sw0 = cases.ball_sweep(N)
-    run("cfg3 Dopri5 bouncing ball, state events on device", "ball", "Dopri5", y0, p, sw0, 3.0, 81 * 2 + 20,
-        rtol=1e-6, atol=1e-6)
-    y0, p = cases.robertson_sweep(1 << 18)
-    run("cfg4 Radau5ODE Robertson, analytic Jacobian", "robertson", "Radau5ODE", y0, p, None, 40.0, 1040,
-        rtol=1e-6, atol=np.array(cases.ROBERTSON_ATOL), usejac=1)
-    # the same ensemble with RodasODE (SURVEY 8f-3): ~420 flops per accepted step by the same counting convention
-    # (6 x (RHS + back-substitution), LU, Jacobian, df/dt difference, stage combinations, CONTRO coefficients)
-    run("cfg4' RodasODE Robertson, analytic Jacobian", "robertson", "RodasODE", y0, p, None, 40.0, 420,
-        rtol=1e-6, atol=np.array(cases.ROBERTSON_ATOL), usejac=1)
-    y0, p = cases.gyro_sweep(1 << 22)
-    run("cfg5 Dopri5 gyro (12 states), dense output every 1e-3", "gyro", "Dopri5", y0, p, None, 0.1,
-        81 * 12 + 6 * 39 + 20, t_grid=np.linspace(0.0, 0.1, 101)[1:], rtol=1e-8, atol=1e-8)
-    run("cfg5' the same with the 100 rows reduced over the ensemble in the kernel (mean/var/min/max, no dense buffer)",
-        "gyro", "Dopri5", y0, p, None, 0.1, 81 * 12 + 6 * 39 + 20, t_grid=np.linspace(0.0, 0.1, 101)[1:],
-        reduce_rows=True, rtol=1e-8, atol=1e-8)
-    return out
+def run_other_configs(device, peak_tflops, hbm_gbs):
+    """cfg 2-5 of BASELINE.json at full size on one GPU (the `configs` key of the headline line)."""
+    return [run_config(device, cfg, 0, 1, peak_tflops, hbm_gbs) for cfg in config_table().values()]
+
+
+def main_config(a, rank, world, local_rank):
+    """--config NAME: one of the other BASELINE configurations as the timed workload, at any number of GPUs (weak
+    scaling: every GPU integrates the configuration's member count, dealt from the world-sized sweep)."""
+    import torch
+    import torch.distributed as dist
+    from assimulo_b200.gpu import _core
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    cfg = config_table()[a.config]
+    peak_tflops, _ = _core.measure_fp64_peak(local_rank, 0.5)
+    hbm = measured_hbm()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    rec = run_config(local_rank, cfg, rank, world, peak_tflops, hbm, steps=a.steps, warmup=max(a.warmup, 1))
+    vals = torch.tensor([rec["kernel_ms"]], dtype=torch.float64, device="cuda")
+    work = torch.tensor([float(rec["accepted_steps"]), float(rec["not_complete"])], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(vals, op=dist.ReduceOp.MAX)
+        dist.all_reduce(work, op=dist.ReduceOp.SUM)
+    ms = float(vals[0])
+    steps_all, nbad = float(work[0]), int(work[1])
+    if rank == 0:
+        hbm_bound = "hbm_write_frac" in rec
+        line = {"metric": "accepted trajectory-steps/sec (%s, whole box)" % cfg["title"], "value": steps_all / (ms * 1e-3),
+                "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 1), "ms_per_step": ms,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": cfg["title"], "members_per_gpu": cfg["members"], "members_total": cfg["members"] * world,
+                           "solver": cfg["solver"], "model": cfg["model"],
+                           "timing": "kernel launches only (CUDA events on the launching stream), max over ranks of the "
+                                     "per-rank mean; inputs resident in HBM"},
+                "not_complete": nbad, "gpu_launches": rec["gpu_launches"], "rank0": rec,
+                "roofline": ({"bound": "hbm", "achieved": rec["dense_bytes"] / (ms * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
+                              "frac": rec["dense_bytes"] / (ms * 1e-3) / 1e9 / hbm, "traffic": None} if hbm_bound else
+                             {"bound": "fp64_fma", "achieved": rec["accepted_steps"] * rec["flops_per_accepted_step"] / (ms * 1e-3) / 1e12,
+                              "peak": peak_tflops, "unit": "TFLOP/s",
+                              "frac": rec["accepted_steps"] * rec["flops_per_accepted_step"] / (ms * 1e-3) / 1e12 / peak_tflops,
+                              "traffic": None, "flops_per_accepted_step": rec["flops_per_accepted_step"]})}
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def measured_hbm():
+    try:
+        return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+    except Exception:
+        return 6457.4
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -381,115 +476,194 @@ def main_gpu(a, rank, world, local_rank):
     # CUDA event pair on the launching stream; the library keeps the last 64 pairs) ----
     kernel_ms = h.kernel_ms_history(min(a.steps, 64))
 
-    # ---- e2e: the public solver API with HOST buffers; H2D + kernel + D2H inside every step ----
+    # ---- what the host link sustains with all ranks busy at once (the ceiling e2e is judged against) ----
+    link = {}
+    for mode in range(6):
+        barrier()
+        link[mode] = _core.measure_hostlink(local_rank, 1 << 27, mode, 0.12)
+    link_t = torch.tensor([link[m] for m in range(6)], dtype=torch.float64, device="cuda")
+    link_min, link_sum = link_t.clone(), link_t.clone()
+    if world > 1:
+        dist.all_reduce(link_min, op=dist.ReduceOp.MIN)
+        dist.all_reduce(link_sum, op=dist.ReduceOp.SUM)
+    link_min, link_sum = [float(v) for v in link_min.cpu()], [float(v) for v in link_sum.cpu()]
+
+    # ---- e2e: the public solver API with HOST buffers; H2D + kernel + D2H inside every step; at N > 1 the step ends
+    # with the path's one collective, the all-gather of {t, y, status} over NCCL issued by the library ----
+    from assimulo_b200.gpu import parallel
+    GATHER_WHAT = _core.GATHER_T | _core.GATHER_Y | _core.GATHER_STATUS
+
+    def make_sim(problem):
+        sm = Dopri5(problem, device=local_rank)
+        sm.rtol, sm.atol = RTOL, ATOL
+        sm.order = "two-ended"  # expensive and cheap 32-member batches alternate: even PCIe demand in zero-copy mode
+        sm.options["reuse_buffers"] = True
+        if a.host_chunks:
+            sm.options["host_chunks"] = a.host_chunks
+        return sm
+
+    def make_step(sm):
+        def step():
+            sm.reset()                    # back to (t0, y0): the next simulate() uploads the inputs again
+            sm.simulate(TF)               # H2D inputs / kernel(s) / D2H final states + summary, mode = sm.host_mode
+            assert sm.n_not_complete == 0
+            if world > 1:
+                parallel.allgather_device(sm, GATHER_WHAT)
+                sm._handle.sync()
+            return sm.statistics["nsteps"]
+        return step
+
+    def time_steps(step, k):
+        barrier()
+        t0 = time.perf_counter()
+        n = 0
+        for _ in range(k):
+            n += step()
+        barrier()
+        return time.perf_counter() - t0, n
+
+    def tune(sm, step):
+        """pick the host mode by measurement: which side of the link the SMs or the copy engines drive better depends
+        on the machine and on how many GPUs share it (profiles/r2_pcie.md)"""
+        res = {}
+        for mode in ("zero-copy", "zero-copy-in", "zero-copy-out", "staged"):
+            sm.host_mode = mode
+            step()
+            w, _ = time_steps(step, 2)
+            tw = torch.tensor([w], dtype=torch.float64, device="cuda")
+            if world > 1:
+                dist.all_reduce(tw, op=dist.ReduceOp.MAX)
+            res[mode] = float(tw[0]) / 2 * 1e3
+        best = min(res, key=res.get)
+        sm.host_mode = best
+        return best, res
+
+    # the sweep as a loop over Explicit_Problem(rhs_i, y0) holds it: N identical y0 rows + mu[N].  The problem class
+    # notices the shared row, so only mu crosses PCIe (aens_set_shared_y0); results: y[N, 2] every step.
     prob = Batched_Explicit_Problem(model="vdp", y0=y0_h, p0=p_h)
-    sim = Dopri5(prob, device=local_rank)
-    sim.rtol, sim.atol = RTOL, ATOL
-    sim.order = "two-ended"  # expensive and cheap 32-member batches alternate: even PCIe demand in zero-copy mode
-    sim.options["reuse_buffers"] = True
-    if a.host_chunks:
-        sim.options["host_chunks"] = a.host_chunks
-
-    def e2e_step():
-        sim.reset()                    # back to (t0, y0): the next simulate() uploads y0 and p again
-        sim.simulate(TF)               # chunk-pipelined H2D inputs / kernels / D2H final states + summary
-        assert sim.n_not_complete == 0
-        return sim.statistics["nsteps"]
-
+    assert prob.y0_row is not None
+    sim = make_sim(prob)
+    if world > 1:
+        parallel.comm_init(sim)
+    e2e_step = make_step(sim)
+    e2e_mode, e2e_modes = tune(sim, e2e_step)
     for _ in range(max(1, a.warmup // 2)):
         e2e_step()
-    barrier()
-    t0 = time.perf_counter()
-    e2e_steps = 0
-    for _ in range(a.steps):
-        e2e_steps += e2e_step()
-    barrier()
-    e2e_wall = time.perf_counter() - t0
-    # the same sweep given the way it is specified -- ONE initial state [2, -0.6] for all members plus mu[N]: the row
-    # travels in the kernel's argument block (aens_set_shared_y0), only mu crosses PCIe (extra key e2e_shared_y0)
-    prob2 = Batched_Explicit_Problem(model="vdp", y0=[2.0, -0.6], p0=p_h)
-    sim2 = Dopri5(prob2, device=local_rank)
-    sim2.rtol, sim2.atol = RTOL, ATOL
-    sim2.order = "two-ended"
-    sim2.options["reuse_buffers"] = True
+    e2e_wall, e2e_steps = time_steps(e2e_step, a.steps)
+    gather_ms = sim._handle.last_gather_ms() if world > 1 else 0.0
+    # the general case: every member with its own initial state (y0[N, 2] uploaded every step); extra key
+    prob2 = Batched_Explicit_Problem(model="vdp", y0=y0_h, p0=p_h, detect_shared_y0=False)
+    sim2 = make_sim(prob2)
+    if world > 1:
+        parallel.comm_init(sim2)
+    e2e2_step = make_step(sim2)
+    e2e2_mode, e2e2_modes = tune(sim2, e2e2_step)
+    e2e2_wall, e2e2_steps = time_steps(e2e2_step, a.steps)
+    h2d = N * 8 + 16                     # p[N,1] + the shared y0 row
+    h2d2 = N * 3 * 8                     # y0[N,2], p[N,1]
+    d2h = N * 2 * 8 + 96                 # y[N,2] + statistic sums and the not-complete count (t, status: on demand)
 
-    def e2e2_step():
-        sim2.reset()
-        sim2.simulate(TF)
-        assert sim2.n_not_complete == 0
-        return sim2.statistics["nsteps"]
-
-    for _ in range(max(1, a.warmup // 2)):
-        e2e2_step()
-    barrier()
-    t0 = time.perf_counter()
-    e2e2_steps = 0
-    for _ in range(a.steps):
-        e2e2_steps += e2e2_step()
-    barrier()
-    e2e2_wall = time.perf_counter() - t0
-    h2d = N * 3 * 8                      # y0[N,2], p[N,1]
-    d2h = N * 2 * 8 + 72                 # y[N,2] + statistic sums and the not-complete count (t, status: on demand)
+    # ---- the all-gather checked on hardware: a strided sample of the GATHERED members against a fresh single-GPU
+    # integration of the same members on rank 0 (bit-identical: members do not interact) ----
+    gather_check = None
+    if world > 1:
+        g = sim._handle.get_gathered(n_total, want_stats=True)
+        if rank == 0:
+            S = 4096
+            gi = np.linspace(0, n_total - 1, S).astype(np.int64)            # global member indices
+            chunk, lane = gi // 32, gi % 32
+            pos = (chunk % world) * N + (chunk // world) * 32 + lane         # where the deal put them (rank-major)
+            mu_s = 10.0 ** (-1.0 + 3.0 * gi / max(n_total - 1, 1))
+            hs = _core.Handle(local_rank)
+            hs.set_model_builtin("vdp")
+            hs.set_ensemble(np.tile([2.0, -0.6], (S, 1)), mu_s.reshape(-1, 1), None, 0.0)
+            hs.set_opts(opts)
+            hs.set_output(None, 0)
+            hs.simulate(TF)
+            ts, ys, _, sts = hs.get_final()
+            ns = hs.get_stats("nsteps")
+            hs.close()
+            gather_check = {"members": S, "max_abs_diff_y": float(np.max(np.abs(g["y"][pos] - ys))),
+                            "nsteps_equal": bool(np.array_equal(g["stats"][0][pos], ns)),
+                            "status_equal": bool(np.array_equal(g["status"][pos], sts)),
+                            "t_equal": bool(np.array_equal(g["t"][pos], ts)),
+                            "all_complete": bool((g["status"] == 0).all()),
+                            "accepted_steps_gathered": int(g["stats"][0].astype(np.int64).sum())}
+            assert gather_check["max_abs_diff_y"] == 0.0 and gather_check["nsteps_equal"] and \
+                gather_check["status_equal"] and gather_check["t_equal"], gather_check
+        del g
 
     # ---- reduce over ranks: MAX time, SUM work ----
-    vals = torch.tensor([total_ms, e2e_wall, float(np.mean(kernel_ms)), e2e2_wall], dtype=torch.float64, device="cuda")
+    vals = torch.tensor([total_ms, e2e_wall, float(np.mean(kernel_ms)), e2e2_wall, gather_ms], dtype=torch.float64,
+                        device="cuda")
     work = torch.tensor([float(steps_rank), float(e2e_steps), float(e2e2_steps)], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(vals, op=dist.ReduceOp.MAX)
         dist.all_reduce(work, op=dist.ReduceOp.SUM)
-    total_ms, e2e_wall, kern_ms, e2e2_wall = [float(v) for v in vals.cpu()]
+    total_ms, e2e_wall, kern_ms, e2e2_wall, gather_ms = [float(v) for v in vals.cpu()]
     steps_all, e2e_steps_all, e2e2_steps_all = [float(v) for v in work.cpu()]
-
-    # final all-gather of the results (the path's only collective; outside the timed region)
-    if world > 1:
-        from assimulo_b200.gpu import parallel
-        g = parallel.gather_final(sim, n_total)
-        assert g["t"].shape[0] == n_total
 
     if rank == 0:
         value = steps_all * a.steps / (total_ms * 1e-3)
         e2e_value = e2e_steps_all / e2e_wall
         achieved = steps_rank * FLOPS_PER_STEP / (kern_ms * 1e-3) / 1e12
+        nominal = 148 * 64 * 2 * 1.965e9 / 1e12
+
+        def floor(h2d_b, d2h_b):
+            """lower bound of one e2e step on this box: the kernel, or the step's bytes at the best rate each direction
+            of the host link sustained with all ranks busy (copy engine or SM-initiated, per-GPU minimum), whichever
+            is longer; plus the all-gather, which follows the kernel"""
+            up = max(link_min[0], link_min[3])
+            down = max(link_min[1], link_min[4])
+            link_ms = max(h2d_b / up, d2h_b / down) / 1e6
+            return {"kernel_ms": kern_ms, "link_ms": link_ms, "gather_ms": gather_ms,
+                    "floor_ms": max(kern_ms, link_ms) + gather_ms}
+        f1, f2 = floor(h2d, d2h), floor(h2d2, d2h)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": total_ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "config": workload_config(a, n_total),
             "accepted_steps_per_pass": steps_all, "kernel_ms": kern_ms,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "ms_per_step": e2e_wall / a.steps * 1e3,
-                    "path": "Dopri5(Batched_Explicit_Problem).simulate() -> aens_simulate_host through the C ABI, "
-                            "zero-copy mode: ONE launch whose warps read their members' y0/p rows from pinned host "
-                            "memory over PCIe when they fetch them and write the final y rows back when they finish"},
-            "e2e_shared_y0": {"value": e2e2_steps_all / e2e2_wall, "unit": UNIT, "h2d_bytes_per_step": int(N * 8 + 16),
-                              "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e2_wall / a.steps * 1e3,
-                              "path": "the same call with the problem given as specified: ONE initial state for all "
-                                      "members (y0=[2,-0.6]) + mu[N]; the row travels in the kernel's argument block "
-                                      "(aens_set_shared_y0), only mu crosses PCIe.  Extra information: the `e2e` key "
-                                      "above keeps the general per-member y0[N,2] upload"},
+                    "ms_per_step": e2e_wall / a.steps * 1e3, "host_mode": e2e_mode, "host_mode_probe_ms": e2e_modes,
+                    "gather_ms": gather_ms, "gather_bytes_per_rank": int(N * 28 + 32) if world > 1 else 0,
+                    "floor": f1, "frac_of_floor": f1["floor_ms"] / (e2e_wall / a.steps * 1e3),
+                    "path": "Dopri5(Batched_Explicit_Problem(y0[N,2], mu[N])).simulate() -> aens_simulate_host through "
+                            "the C ABI with pinned HOST arrays; the problem class detects that all y0 rows are equal, so "
+                            "mu[N] + one row go up and y[N,2] + the summary come down every step; host mode picked by "
+                            "measurement (host_mode_probe_ms)" +
+                            ("; the step ends with ONE ncclAllGather of {t, y, status} issued by the library "
+                             "(aens_allgather_results)" if world > 1 else "")},
+            "e2e_per_member_y0": {"value": e2e2_steps_all / e2e2_wall, "unit": UNIT, "h2d_bytes_per_step": int(h2d2),
+                                  "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e2_wall / a.steps * 1e3,
+                                  "host_mode": e2e2_mode, "host_mode_probe_ms": e2e2_modes, "floor": f2,
+                                  "frac_of_floor": f2["floor_ms"] / (e2e2_wall / a.steps * 1e3),
+                                  "path": "the same call when every member has its own initial state: y0[N,2] is "
+                                          "uploaded every step as well (shared-row detection off).  Extra information"},
+            "hostlink": {"what": "GB/s per GPU with all %d rank(s) transferring at once, 128 MiB pinned buffers "
+                                 "(aens_measure_hostlink): min over ranks / sum over ranks" % world,
+                         "modes": {_core.HOSTLINK_MODES[m]: [link_min[m], link_sum[m]] for m in range(6)}},
+            "gather_check": gather_check,
             "gpu_launches": int(launches),
             "cpu_affinity": ("rank 0 bound to %d CPUs next to its GPU (NVML)" % len(numa)) if numa else "unbound",
             "roofline": {"bound": "fp64_fma", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s",
-                         "frac": achieved / peak_tflops,
+                         "frac": achieved / peak_tflops, "peak_nominal": nominal, "frac_of_nominal": achieved / nominal,
                          "traffic": (ncu_traffic() or (None, None))[0] if a.members == (1 << 23) else None,
                          "traffic_source": "dram bytes read+written by one launch at 2^23 members, ncu --set full, "
                                            "profiles/%s" % (ncu_traffic() or (None, "absent"))[1],
                          "algorithmic_bytes": a.members * ((2 * 2 + 1 + 1 + 1) * 8 + 4 + 9 * 4),
-                         "peak_source": "measured live on this GPU: 1 s of 8-chain DFMA in the full-rate operand "
-                                        "form (aens_measure_fp64_peak, profiles/r1_fp64_pipe.md); "
-                                        "MEASURED_PEAKS.json has no fp64 entry",
+                         "peak_source": "measured live on this GPU by this library (builder's number): 1 s of 8-chain "
+                                        "DFMA in the full-rate operand form (aens_measure_fp64_peak, "
+                                        "profiles/r1_fp64_pipe.md); MEASURED_PEAKS.json has no fp64 entry; "
+                                        "peak_nominal = 148 SM x 64 lanes x 2 x 1.965 GHz",
                          "kernel": "aens_dopri5_d0_vdp_x_f", "flops_per_accepted_step": FLOPS_PER_STEP,
                          "implied_sm_mhz": peak_mhz},
             "clocks": clk,
         }
         if a.other_configs and world == 1:
-            hbm = 6457.4
-            try:
-                hbm = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
-            except Exception:
-                pass
-            del sim, prob
+            del sim, prob, sim2, prob2
             h.close()
-            line["configs"] = run_other_configs(local_rank, peak_tflops, hbm)
+            line["configs"] = run_other_configs(local_rank, peak_tflops, measured_hbm())
         if a.cpu_baseline:
             if getattr(bind_to_gpu_numa_node, "original", None):  # the CPU leg uses every host core again
                 os.sched_setaffinity(0, bind_to_gpu_numa_node.original)
@@ -500,6 +674,7 @@ def main_gpu(a, rank, world, local_rank):
         sys.stdout.flush()
         os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
     return 0
 
@@ -515,7 +690,10 @@ def main():
     ap.add_argument("--host-chunks", type=int, default=0, help="chunks of the e2e host pipeline (0 = library default)")
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
     ap.add_argument("--no-other-configs", dest="other_configs", action="store_false",
-                    help="skip the BASELINE.json configs 2-5 (they run only at --gpus 1)")
+                    help="skip the BASELINE.json configs 2-5 inside the headline line (N = 1 only)")
+    ap.add_argument("--config", default="headline",
+                    help="headline (default) or one of the other BASELINE configurations as the timed workload, at any "
+                         "--gpus: cfg2_rk4 cfg2_rk34 cfg3 cfg4 cfg4_rodas cfg5 cfg5_reduced")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3) if a.impl == "graft" else a.warmup
     rank = int(os.environ.get("RANK", "0"))
@@ -529,6 +707,8 @@ def main():
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(a.gpus),
                "--master-addr", "127.0.0.1", "--master-port", str(29500 + os.getpid() % 1000)] + sys.argv
         return subprocess.call(cmd)
+    if a.config != "headline":
+        return main_config(a, rank, world, local_rank)
     return main_gpu(a, rank, world, local_rank)
 
 

@@ -71,6 +71,8 @@ extern "C" {
 #define AENS_ST_RADAU_STEP_TOO_SMALL (-6)
 #define AENS_ST_RADAU_SINGULAR (-7)   /* also: singular Newton matrix in ImplicitEuler (numpy LinAlgError) */
 #define AENS_ST_NEWTON_FAILED (-8)    /* ImplicitEuler: 'Newton iteration failed' (euler.pyx:415,426) */
+#define AENS_ST_TIME_LIMIT (-9)       /* aens_set_time_limit: the member was not started before the deadline
+                                       * (TimeLimitExceeded, src/explicit_ode.pyx:290-292) */
 
 /* statistics slots for aens_get_stats (names: src/ode.pyx:153-172) */
 #define AENS_STAT_NSTEPS 0           /* accepted steps */
@@ -196,7 +198,10 @@ int aens_simulate_host(aens_handle_t *h, long long N, const double *y0, const do
 /* How aens_simulate_host moves data: 0 = automatic (zero-copy when every host array is page-locked, mapped and
  * 16-byte aligned -- ONE kernel launch whose warps read their members' rows from host memory over PCIe when they
  * fetch them and write the final rows back when they finish; otherwise the chunked staging pipeline),
- * 1 = always the chunked staging pipeline, 2 = zero-copy or fail. */
+ * 1 = always the chunked staging pipeline (copy engine both ways), 2 = zero-copy or fail,
+ * 3 = chunked, inputs zero-copy, results by copy engine, 4 = chunked, inputs by copy engine, results zero-copy
+ * (which side of the host link the SMs or the copy engines drive better depends on the machine and on how many GPUs
+ * share it: profiles/r2_pcie.md). */
 int aens_set_host_mode(aens_handle_t *h, int mode);
 /* Parameter sweeps whose members share one initial state (every Explicit_Problem of the loop built with the same
  * y0): with on != 0 the y0 argument of aens_set_ensemble / aens_simulate_host is ONE row y0[n] instead of
@@ -252,9 +257,47 @@ int aens_stream(aens_handle_t *h, void **stream);
 int aens_host_alloc(long long bytes, void **ptr);
 int aens_host_free(void *ptr);
 
+/* Time limit of one aens_simulate / aens_simulate_host call in seconds of device time, 0 = none (ODE.time_limit,
+ * src/ode.pyx:372-392, checked per step in Explicit_ODE.report_solution, src/explicit_ode.pyx:290-292, where it raises
+ * TimeLimitExceeded).  One launch integrates the whole ensemble, so the limit is checked where the device code has a
+ * natural seam: when a warp asks for its next members.  Members fetched after the deadline are not integrated; they
+ * keep their state and get status AENS_ST_TIME_LIMIT (members already in flight run to completion). */
+int aens_set_time_limit(aens_handle_t *h, double seconds);
+
+/* Multi-GPU: the ensemble shards by contiguous member blocks, one handle (process) per GPU, and the path's ONLY
+ * collective is one all-gather of the final results over NCCL (NVLink 5 / NVSwitch) at the end of simulate()
+ * (handle convention of thirdparty/radau5/radau5.h:6-13: opaque handle, int return, error text on the
+ * handle).  Rank 0 obtains a 128-byte id with aens_comm_unique_id and hands it to the other ranks by any host-side
+ * means (file, socket, MPI, torch.distributed ...); every rank then calls aens_comm_init on its handle.
+ * aens_allgather_results packs the selected SoA result buffers of this rank's block into one record and issues ONE
+ * ncclAllGather on the handle's stream (asynchronous; aens_sync waits); every rank must hold the same number of
+ * members (pad the last block) and select the same fields.  what = 0 selects everything the model has.
+ * aens_get_gathered unpacks the gathered records on the device and returns the first n_total members in rank order as
+ * host arrays (any pointer may be NULL): t[n_total], y[n_total][n], status[n_total], stats[AENS_NSTATS][n_total],
+ * ev_t[n_total][event_slots], ev_info[n_total][event_slots].  aens_gathered_ptr exposes the raw gathered buffer
+ * ([nranks] records of rec_bytes each) to device-side consumers. */
+#define AENS_COMM_ID_BYTES 128
+#define AENS_GATHER_T 1
+#define AENS_GATHER_Y 2
+#define AENS_GATHER_STATUS 4
+#define AENS_GATHER_STATS 8
+#define AENS_GATHER_EVENTS 16
+int aens_comm_unique_id(void *id128);
+int aens_comm_init(aens_handle_t *h, int rank, int nranks, const void *id128);
+int aens_comm_destroy(aens_handle_t *h);
+int aens_allgather_results(aens_handle_t *h, int what);
+int aens_last_gather_ms(aens_handle_t *h, float *ms);
+int aens_gathered_ptr(aens_handle_t *h, void **ptr, long long *rec_bytes, int *nranks);
+int aens_get_gathered(aens_handle_t *h, long long n_total, double *t, double *y, int *status, int *stats,
+                      double *ev_t, int *ev_info);
+
 /* Measurement helpers (not on the product path): sustained fp64 FMA throughput of the device measured with a
  * dependent-chain DFMA kernel for ~`seconds`; result in TFLOP/s (2 flops per DFMA). */
 int aens_measure_fp64_peak(int device, double seconds, double *tflops, double *sm_clock_mhz_est);
+/* What the host link of `device` sustains with `bytes`-sized page-locked buffers for ~`seconds`, in GB/s:
+ * mode 0 copy engine host->device, 1 copy engine device->host, 2 both at once (sum of both directions),
+ * 3 SM-initiated reads of mapped host memory (what the zero-copy host mode does), 4 SM-initiated writes, 5 both. */
+int aens_measure_hostlink(int device, long long bytes, int mode, double seconds, double *gbs);
 /* compile-only check of a model source with NVRTC for sm_100a (needs no GPU); returns the cubin size in bytes
  * (> 0) or a negative AENS_ERR_* with the compiler log in errbuf */
 long long aens_nvrtc_check(const char *cuda_src, int n, int n_p, int n_g, int n_sw, int has_jac, int strict,

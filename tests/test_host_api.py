@@ -212,7 +212,12 @@ def test_shared_initial_state_bookkeeping_without_a_device():
     mu = np.linspace(0.1, 10.0, 50)[:, None]
     prob = Batched_Explicit_Problem(model="vdp", y0=[2.0, -0.6], p0=mu)
     assert prob.N == 50 and prob.y0.shape == (50, 2) and np.array_equal(prob.y0_row, [2.0, -0.6])
-    assert Batched_Explicit_Problem(model="vdp", y0=np.tile([2.0, -0.6], (50, 1)), p0=mu).y0_row is None
+    # the same sweep written the long way (N identical rows) is recognised, unless the caller opts out
+    assert np.array_equal(Batched_Explicit_Problem(model="vdp", y0=np.tile([2.0, -0.6], (50, 1)), p0=mu).y0_row, [2.0, -0.6])
+    assert Batched_Explicit_Problem(model="vdp", y0=np.tile([2.0, -0.6], (50, 1)), p0=mu, detect_shared_y0=False).y0_row is None
+    rows = np.tile([2.0, -0.6], (50, 1))
+    rows[17, 1] = -0.6000000000000001
+    assert Batched_Explicit_Problem(model="vdp", y0=rows, p0=mu).y0_row is None
     assert Batched_Explicit_Problem(model="vdp", y0=[2.0, -0.6]).y0_row is None          # a single member is just a member
     sim = Dopri5(prob)
     assert np.array_equal(sim._y_row, [2.0, -0.6]) and sim.y.shape == (50, 2)

@@ -49,9 +49,12 @@ def _oracle_rows(y0, mu):
 
 
 class _RowStats(object):
-    """what a solver with reduce_rows = True holds after simulate(): the statistics of its own block"""
+    """what a solver with reduce_rows = True holds after simulate(): the statistics of ALL members of the shard
+    problem it was built on (copies appended by padding included -- which is why padded shards are refused)"""
 
-    def __init__(self, rows):
+    def __init__(self, problem):
+        rows = _oracle_rows(problem.y0, problem.p0)
+        self.problem, self.N = problem, problem.N
         self.row_statistics = {"mean": rows.mean(axis=1), "var": rows.var(axis=1), "min": rows.min(axis=1),
                                "max": rows.max(axis=1), "count": np.full(rows.shape[0], rows.shape[1]), "t": GRID}
 
@@ -76,7 +79,24 @@ def _worker(rank, port, q):
     ball = parallel.shard_problem(Batched_Explicit_Problem(model="ball", y0=y0b, p0=pb, sw0=swb), rank, WORLD)
     gb = parallel.gather_final(_OracleBackedSolver(ball), N)
     # row reduction mode: each rank contributes the [rows, n] statistics of its block, never the rows
-    rs = parallel.gather_row_statistics(_RowStats(_oracle_rows(y0[lo:hi], mu[lo:hi])))
+    # (reduced over the members of the shard problem itself: the shard must be unpadded, a padded one is refused)
+    padded_refused = True
+    if shard.n_valid != shard.N:
+        try:
+            parallel.gather_row_statistics(_RowStats(shard))
+            padded_refused = False
+        except ValueError:
+            pass
+    assert padded_refused
+    exact = parallel.shard_problem(full, rank, WORLD, pad=False)
+    assert exact.N == hi - lo == exact.n_valid
+    rs = parallel.gather_row_statistics(_RowStats(exact))
+    # more ranks than members: the empty rank contributes nothing
+    tiny = Batched_Explicit_Problem(model="vdp", y0=y0[:1], p0=mu[:1])
+    tshard = parallel.shard_problem(tiny, rank, WORLD, pad=False)
+    assert (tshard is None) == (rank > 0)
+    rs1 = parallel.gather_row_statistics(_RowStats(tshard) if tshard is not None else None)
+    assert (rs1["count"] == 1).all()
     q.put((rank, g["y"], g["t"], g["status"], g["statistics"]["nsteps"], g["stats_per_member"]["nsteps"],
            gb["y"], gb["event_count"], gb["event_t"], gb["event_info"], rs))
     dist.barrier()

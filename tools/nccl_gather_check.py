@@ -1,8 +1,9 @@
 #!/usr/bin/env python
 """Multi-GPU check of the path's only collective (run under torchrun on N GPUs):
 every rank integrates its contiguous block of a bouncing-ball ensemble (state events) on its own GPU,
-parallel.gather_final all-gathers {t, y, status, stats, event times} over NCCL straight from the library's device
-buffers, and every rank compares the assembled result with the CPU oracle."""
+parallel.gather_final all-gathers {t, y, status, stats, event times} with the library's own ncclAllGather
+(aens_comm_init / aens_allgather_results / aens_get_gathered: torch.distributed only carries the communicator id),
+and every rank compares the assembled result with the CPU oracle.  tests/test_gpu_round2.py runs it on 2 GPUs."""
 import os
 import sys
 
