@@ -98,8 +98,12 @@ class Batched_Explicit_Problem(object):
         if self.n_sw:
             if sw0 is None:
                 sw0 = self._default_sw0()
-            sw0 = np.asarray(sw0, dtype=bool)
-            self.sw0 = np.ascontiguousarray(np.broadcast_to(sw0.reshape(-1, self.n_sw), (N, self.n_sw))).astype(np.uint8)
+            raw = np.asarray(sw0)
+            if raw.dtype == np.uint8 and raw.shape == (N, self.n_sw) and raw.flags.c_contiguous and raw.max(initial=0) <= 1:
+                self.sw0 = raw   # already in the device's form: kept as it is (it may be page-locked memory)
+            else:
+                sw0 = np.asarray(sw0, dtype=bool)
+                self.sw0 = np.ascontiguousarray(np.broadcast_to(sw0.reshape(-1, self.n_sw), (N, self.n_sw))).astype(np.uint8)
         else:
             self.sw0 = np.zeros((N, 0), dtype=np.uint8)
 

@@ -81,9 +81,12 @@ class Batched_Explicit_ODE(object):
         self.t0 = problem.t0
         self.t = problem.t0
         self.N = problem.N
-        self.y = problem.y0.copy()
+        # no defensive copies of ensemble-sized arrays (they are only read when uploaded): if the caller built the problem
+        # on page-locked arrays, the very first simulate() can already hand them to the device as they are
+        self.y = problem.y0
         self._y_row = problem.y0_row   # set while every member still sits at one shared initial state
         self.sw = problem.sw0.astype(bool)
+        self._sw_in = problem.sw0      # the uint8 array the device reads (self.sw is the reference's bool view of it)
         self._status = None        # per-member arrays are materialised on first access (see the properties)
         self._t_members = None
         self._events = None
@@ -145,8 +148,12 @@ class Batched_Explicit_ODE(object):
             if self.y.shape[0] != self.N:
                 raise Explicit_ODE_Exception("y0 must have shape [n] or [N, n] with N = %d." % self.N)
         if sw0 is not None:
-            self.sw = np.ascontiguousarray(np.broadcast_to(np.asarray(sw0, dtype=bool).reshape(-1, self.problem.n_sw),
-                                                           (self.N, self.problem.n_sw)))
+            if sw0 is self.problem.sw0:
+                self._sw_in = sw0
+            else:
+                self._sw_in = np.ascontiguousarray(np.broadcast_to(
+                    np.asarray(sw0, dtype=bool).reshape(-1, self.problem.n_sw), (self.N, self.problem.n_sw))).astype(np.uint8)
+            self.sw = self._sw_in.astype(bool)
         self._status, self._t_members, self._events = None, None, None
         self.n_not_complete = 0
         self._dirty = True
@@ -219,12 +226,25 @@ class Batched_Explicit_ODE(object):
             nch = self.options["host_chunks"] or max(1, min(32, self.N >> 19))
             h.set_output(None, int(self.options["event_slots"]))
             h.set_schedule(int(self.options["refill_threshold"]), None)
-            y = pin[1] if pin is not None else np.empty((self.N, self._leny))
-            sw = np.empty((self.N, self.problem.n_sw), dtype=np.uint8) if self.problem.n_sw else None
+            zc_out = self.options["host_mode"] in ("zero-copy", "zero-copy-out")
+            if pin is not None:
+                y = pin[1]
+            elif zc_out:   # the kernel writes the final rows itself: they must land in page-locked memory
+                y = _core().pinned_empty((self.N, self._leny), np.float64)
+            else:
+                y = np.empty((self.N, self._leny))
+            sw = None
+            if self.problem.n_sw:
+                if pin is not None or zc_out:
+                    if getattr(self, "_pin_sw", None) is None or self._pin_sw.shape[0] != self.N:
+                        self._pin_sw = _core().pinned_empty((self.N, self.problem.n_sw), np.uint8)
+                    sw = self._pin_sw
+                else:
+                    sw = np.empty((self.N, self.problem.n_sw), dtype=np.uint8)
             # a sweep whose members share one initial state sends that row, not [N, n] (aens_set_shared_y0)
             y_in = self._y_row if self._y_row is not None else self.y
             sums, nbad = h.simulate_host(y_in, self.problem.p0 if self.problem.n_p else None,
-                                         self.sw.astype(np.uint8) if self.problem.n_sw else None, self.t, tfinal,
+                                         self._sw_in if self.problem.n_sw else None, self.t, tfinal,
                                          out_y=y, out_sw=sw, nchunks=int(nch), N=self.N)
             self._y_row = None
             self._dirty = False
@@ -236,7 +256,7 @@ class Batched_Explicit_ODE(object):
             if self._dirty:
                 h.set_ensemble(self._y_row if self._y_row is not None else self.y,
                                self.problem.p0 if self.problem.n_p else None,
-                               self.sw.astype(np.uint8) if self.problem.n_sw else None, self.t, N=self.N)
+                               self._sw_in if self.problem.n_sw else None, self.t, N=self.N)
                 self._dirty = False
             self._y_row = None
             reduce_rows = bool(self.options["reduce_rows"]) and output_list is not None
@@ -259,6 +279,7 @@ class Batched_Explicit_ODE(object):
         self.n_not_complete = int(nbad)
         if sw is not None:
             self.sw = sw.astype(bool)
+            self._sw_in = sw
         for k in STAT_NAMES:
             self.statistics[k] = int(sums[k])
         self.row_statistics = None

@@ -144,7 +144,7 @@ def test_nvrtc_user_model_equals_builtin():
     for s in (a, b):
         s.arith = "strict"          # fast arithmetic too: the second cubin is compiled on demand
         s.simulate(3.0)
-    assert np.array_equal(a.y, b.y) and np.array_equal(a.event_log[1], b.event_log[1])
+    assert np.array_equal(a.y, b.y) and np.array_equal(a.event_log[1], b.event_log[1], equal_nan=True)   # unused slots read NaN
     b.arith = "fast"
     b.reset()
     b.simulate(3.0)

@@ -79,9 +79,12 @@ def test_row_reduction_survives_a_continuation_call():
     two.simulate(2.0)
     b = two.get_row_reduction()
     assert (b["count"] == N).all()
-    first = grid <= 0.83                                   # rows of the first call: the very same integration
-    assert np.array_equal(b["min"][first], a["min"][first]) and np.array_equal(b["max"][first], a["max"][first])
-    assert np.allclose(b["mean"][first], a["mean"][first], rtol=1e-13, atol=1e-14)
+    # rows of the first call: the very same integration, except for the last steps before 0.83, which the first call
+    # clips to its own end point (dopri5.f:411-414) -- rows well before that are identical
+    early = grid <= 0.3
+    assert early.sum() >= 5
+    assert np.array_equal(b["min"][early], a["min"][early]) and np.array_equal(b["max"][early], a["max"][early])
+    assert np.allclose(b["mean"][early], a["mean"][early], rtol=1e-13, atol=1e-14)
     # rows of the second call come from a restarted solver (HINIT again at 0.83): close, not identical
     assert np.allclose(b["mean"], a["mean"], rtol=1e-4, atol=1e-5)
     # a reset starts the records afresh
