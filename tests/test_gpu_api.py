@@ -684,12 +684,12 @@ def test_shared_initial_state_row_equals_the_expanded_array(mode):
     _, mu = cases.vdp_sweep(N)
     mu_p = _core.pinned_empty((N, 1))
     mu_p[:] = mu
-    full = Dopri5(Batched_Explicit_Problem(model="vdp", y0=np.tile([2.0, -0.6], (N, 1)), p0=mu_p))
+    full = Dopri5(Batched_Explicit_Problem(model="vdp", y0=np.tile([2.0, -0.6], (N, 1)), p0=mu_p, detect_shared_y0=False))
     row = Dopri5(Batched_Explicit_Problem(model="vdp", y0=[2.0, -0.6], p0=mu_p))
     assert row.problem.y0_row is not None and full.problem.y0_row is None and row.y.shape == (N, 2)
     for s in (full, row):
         s.options["reuse_buffers"] = True      # pinned result buffers: zero-copy mode is possible
-    row._get_handle().set_host_mode(mode)      # (the expanded array of `full` is pageable: automatic mode)
+    row.host_mode = ("auto", "staged", "zero-copy")[mode]   # (the expanded array of `full` is pageable: automatic mode)
     yf = np.array(full.simulate(2.0)[1][-1])
     yr = np.array(row.simulate(2.0)[1][-1])
     assert np.array_equal(yf, yr) and full.statistics["nsteps"] == row.statistics["nsteps"]
