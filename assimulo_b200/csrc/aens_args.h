@@ -64,6 +64,12 @@ typedef struct {
      * unintegrated with status AENS_ST_TIME_LIMIT. */
     unsigned long long limit_ns;
     unsigned long long *t_start; /* start time of the simulate() call, shared by all launches of a chunked call */
+    /* Radau5ODE: the tolerance transform of radau5_solve (radau5.c:192-216) depends on the options only, so the host
+     * evaluates it once (with glibc's pow, like the reference) and the kernel reads it from the constant bank instead
+     * of carrying it in registers: rtol' = 0.1 rtol^(2/3), atol'_i = rtol' atol_i / rtol, the automatic fnewt, and
+     * cfac = safe (2 newt + 1) (radau5.c:348). */
+    double rd_rtol1, rd_fnewt, rd_cfac;
+    double rd_atol1[AENS_MAX_N];
 } aens_args_t;
 
 #endif

@@ -6,6 +6,7 @@
  */
 #include "aens_device.cuh"
 #include "aens_radau5.cuh"
+#include "aens_split.cuh"
 
 #define AENS_CAT_(a, b) a##b
 #define AENS_CAT(a, b) AENS_CAT_(a, b)
@@ -56,6 +57,20 @@ AENS_DEFINE_KERNEL(KN(aens_rk34_d0_), RK34, KM, kEvents, AENS_MB_RK34)
 AENS_DEFINE_KERNEL(KN(aens_dopri5_d0_), Dopri5, KM, kEvents, AENS_MB_DOPRI5)
 AENS_DEFINE_KERNEL(KN(aens_radau5_d0_), Radau5, KM, kEvents, AENS_MB_RADAU5)
 AENS_DEFINE_KERNEL(KN(aens_impleuler_d0_), ImplEuler, KM, kEvents, AENS_MB_EULER)
+
+/* sub-warp-per-member Dopri5 (aens_split.cuh) for the models that define rhs_g; FAST build only */
+#ifndef AENS_MB_SPLIT
+#define AENS_MB_SPLIT 1
+#endif
+#if defined(AENS_KSPLIT) && !AENS_STRICT
+AENS_DEFINE_SPLIT_KERNEL(KN(aens_dopri5g_d0_), KM, 0, AENS_MB_SPLIT)
+AENS_DEFINE_SPLIT_KERNEL(KN(aens_dopri5g_d1_), KM, 1, AENS_MB_SPLIT)
+extern "C" const void *AENS_CAT(AENS_CAT(aens_kernels_split_, AENS_KNAME), AENS_SUF)(int solver, int dense, int *lanes) {
+    if (lanes) *lanes = KM::G;
+    if (solver != AENS_SOLVER_DOPRI5 || dense == 2) return nullptr;
+    return dense ? (const void *)KN(aens_dopri5g_d1_) : (const void *)KN(aens_dopri5g_d0_);
+}
+#endif
 
 extern "C" const void *AENS_CAT(AENS_CAT(aens_kernels_, AENS_KNAME), AENS_SUF)(int solver, int dense) {
 #define AENS_PICK(base) (dense == 2 ? (const void *)KN(base##d2_) : dense ? (const void *)KN(base##d1_) : (const void *)KN(base##d0_))

@@ -35,6 +35,10 @@ struct AensModelDefaults {
      * Runge-Kutta stages of the FAST Dopri5 build only ever need h * k_j; a model whose f is a product with a
      * parameter can fold h into that factor once per step (Van der Pol: (h mu) * w instead of h * (mu * w)). */
     static constexpr bool HAS_RHS_H = false;
+    /* sub-warp-per-member variant (aens_split.cuh): G lanes share one member, each owning NL of its components;
+     * comp(j, c) = state index of component c of lane j, rhs_g() = this lane's part of f, fetching what it needs from
+     * the other lanes of its group with warp shuffles.  G = 1: the model has no such form. */
+    static constexpr int G = 1, NL = 0;
     static AENS_DEV void prep(double *) {}
     static AENS_DEV double time_events(double, const double *, const unsigned char *, const double *) {
         return AENS_NO_TIME_EVENT;
@@ -128,6 +132,20 @@ struct AensGyro : AensModelDefaults {
             ud[9 + c] = om1 * q0 + (-om0) * q1;
         }
     }
+#if !(defined(AENS_STRICT) && AENS_STRICT)
+    /* Four lanes per member: lane 0 owns the body angular momentum pi = u[0..2], lane 1 + c owns column c of the
+     * rotation matrix, (u[3+c], u[6+c], u[9+c]).  Every lane rotates its own 3-vector v: v' = curl(omega) v with
+     * omega = pi / I fetched from lane 0 -- the same instructions in all four lanes (p = 1/I after prep()). */
+    static constexpr int G = 4, NL = 3;
+    static AENS_DEV int comp(int j, int c) { return j == 0 ? c : 3 + 3 * c + (j - 1); }
+    static AENS_DEV void rhs_g(unsigned gm, int, double, const double *v, const double *p, double *vd) {
+        const double om0 = __shfl_sync(gm, v[0], 0, 4) * p[0], om1 = __shfl_sync(gm, v[1], 0, 4) * p[1],
+                     om2 = __shfl_sync(gm, v[2], 0, 4) * p[2];
+        vd[0] = om2 * v[1] + (-om1) * v[2];
+        vd[1] = (-om2) * v[0] + om0 * v[2];
+        vd[2] = om1 * v[0] + (-om0) * v[1];
+    }
+#endif
     static AENS_DEV void jac(double, const double *, const unsigned char *, const double *, double *) {}
     static AENS_DEV void events(double, const double *, const unsigned char *, const double *, double *) {}
     static AENS_DEV int handle_event(double, double *, unsigned char *, const int *, const double *) { return 0; }

@@ -85,6 +85,8 @@ cdef extern from "assimulo_cuda.h":
     int aens_get_row_reduction(aens_handle_t *h, double *mean, double *var, double *mn, double *mx,
                                long long *count) nogil
     int aens_set_time_limit(aens_handle_t *h, double seconds) nogil
+    int aens_set_lanes_per_member(aens_handle_t *h, int lanes) nogil
+    int aens_last_lanes_per_member(const aens_handle_t *h) nogil
     int aens_comm_unique_id(void *id128) nogil
     int aens_comm_init(aens_handle_t *h, int rank, int nranks, const void *id128) nogil
     int aens_comm_destroy(aens_handle_t *h) nogil
@@ -378,6 +380,13 @@ cdef class Handle:
         with nogil:
             rc = aens_simulate(self.h, tfinal)
         self._check(rc)
+
+    def set_lanes_per_member(self, int lanes):
+        """0 automatic, 1 one thread per member, > 1 the model's sub-warp-per-member kernel or an error."""
+        self._check(aens_set_lanes_per_member(self.h, lanes))
+
+    def last_lanes_per_member(self):
+        return aens_last_lanes_per_member(self.h)
 
     def set_time_limit(self, double seconds):
         """ODE.time_limit: members a warp fetches later than `seconds` after the launch started are not integrated

@@ -67,7 +67,8 @@ class Batched_Explicit_ODE(object):
         self.options = {"report_continuously": False, "display_progress": True, "verbosity": 30, "backward": False,
                         "store_event_points": True, "time_limit": 0, "clock_step": False, "num_threads": 1,
                         "arith": "fast", "refill_threshold": 32, "order": None, "event_slots": 16,
-                        "reuse_buffers": False, "host_chunks": None, "reduce_rows": False, "host_mode": "auto"}
+                        "reuse_buffers": False, "host_chunks": None, "reduce_rows": False, "host_mode": "auto",
+                        "lanes_per_member": 0}
         self.supports = {"state_events": False, "interpolated_output": False, "report_continuously": False}
         self.problem_info = {"dim": problem.n, "dimRoot": problem.n_g, "state_events": problem.n_g > 0,
                              "jac_fcn": problem.has_jac, "switches": problem.n_sw > 0}
@@ -208,6 +209,7 @@ class Batched_Explicit_ODE(object):
         h.set_fetch_reverse(reverse)
         h.set_opts(self._opts_dict())
         h.set_time_limit(float(self.options["time_limit"] or 0.0))
+        h.set_lanes_per_member(int(self.options["lanes_per_member"]))
         h.set_host_mode(HOST_MODES[self.options["host_mode"]])
         pin = None
         if self.options["reuse_buffers"]:
@@ -476,6 +478,15 @@ class Batched_Explicit_ODE(object):
                          doc="How simulate() moves host arrays when inputs and results live in host memory: 'auto' / "
                              "'zero-copy' (one launch, the warps read and write page-locked host memory themselves), "
                              "'staged' (chunked copy-engine pipeline), 'zero-copy-in' / 'zero-copy-out' (one side each).")
+
+    def _set_lanes(self, v):
+        v = int(v)
+        if not 0 <= v <= 32:
+            raise AssimuloException("lanes_per_member must be 0 (automatic), 1 or the model's group size.")
+        self.options["lanes_per_member"] = v
+    lanes_per_member = property(lambda self: self.options["lanes_per_member"], _set_lanes,
+                                doc="0: the library chooses between one thread per member and, for models that define "
+                                    "it (gyro: 4 lanes x 3 states), the sub-warp-per-member kernel; 1 / G force one.")
 
     def _get_reduce_rows(self):
         """True: the rows of the output grid (ncp / ncp_list) are reduced over the ensemble inside the integration

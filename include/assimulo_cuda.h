@@ -166,6 +166,15 @@ int aens_set_output(aens_handle_t *h, int n_out, const double *t_out, int event_
  * permutation of 0..N-1 giving the fetch order (e.g. most expensive first). */
 int aens_set_schedule(aens_handle_t *h, int refill_threshold, const int *order);
 
+/* Lanes per member.  The kernels integrate one member per thread; models with a larger state that define the
+ * cooperative form of their right-hand side (built-in: "gyro", 4 lanes x 3 components) also have a
+ * sub-warp-per-member Dopri5 kernel that keeps a quarter of the state in each lane's registers (csrc/aens_split.cuh).
+ * lanes = 0 (default): the library picks -- the cooperative kernel where one exists and applies (FAST arithmetic,
+ * no row reduction, not the one-call host modes); 1: always one thread per member; > 1: that many lanes or
+ * AENS_ERR_UNSUPPORTED.  aens_last_lanes_per_member reports what the most recent launch used. */
+int aens_set_lanes_per_member(aens_handle_t *h, int lanes);
+int aens_last_lanes_per_member(const aens_handle_t *h);
+
 /* No fetch permutation: hand members out from the highest index downwards (reverse = 1) instead of upwards --
  * for ensembles whose cost grows with the member index (most expensive first, no permutation array to upload) -- or
  * in 32-member batches alternately from the top and the bottom of the range (reverse = 2): for such ensembles in

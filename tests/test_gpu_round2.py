@@ -315,3 +315,82 @@ def test_hostlink_probe_reports_plausible_rates():
     for mode in range(6):
         gbs = _core.measure_hostlink(0, 1 << 26, mode, 0.05)
         assert 1.0 < gbs < 200.0, (mode, gbs)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# sub-warp-per-member Dopri5 (csrc/aens_split.cuh): 4 lanes x 3 states of the gyroscope
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("N", [1, 7, 8, 33, 5000])
+def test_split_dopri5_gyro_matches_oracle_and_thread_per_member(N):
+    from assimulo_b200.gpu import _core
+    y0, p = cases.gyro_sweep(max(N, 2))
+    y0, p = y0[:N], p[:N]
+    o = O.simulate("gyro", "Dopri5", y0, p, tf=0.1, rtol=1e-8, atol=1e-8)
+    res = {}
+    for lanes in (1, 4, 0):
+        h = _handle("gyro", "Dopri5", y0, p, rtol=1e-8, atol=1e-8)
+        h.set_lanes_per_member(lanes)
+        h.simulate(0.1)
+        assert h.last_lanes_per_member() == (1 if lanes == 1 else 4)      # automatic = the cooperative kernel
+        t, y, _, st = h.get_final()
+        res[lanes] = (y, h.get_stats("nsteps"), h.get_stats("nfcns"), h.get_stats("nerrfails"))
+        assert (st == 0).all() and (t == 0.1).all()
+        assert rel_err(y, o["y"]) <= 1e-7                                    # 10 x rtol
+        assert abs(int(res[lanes][1].sum()) - int(o["stats"]["nsteps"].sum())) <= max(1, 0.02 * o["stats"]["nsteps"].sum())
+        h.close()
+    # same arithmetic per component, only the summation order of the norms differs: the two kernels agree far below rtol
+    assert rel_err(res[4][0], res[1][0]) <= 1e-10
+    assert np.array_equal(res[0][0], res[4][0])
+
+
+def test_split_dopri5_gyro_dense_rows_order_and_continuation():
+    from assimulo_b200.gpu import _core
+    N = 1000
+    y0, p = cases.gyro_sweep(N)
+    grid = np.linspace(0.0, 0.1, 21)
+    o = O.simulate("gyro", "Dopri5", y0, p, tf=0.1, t_grid=grid[1:], rtol=1e-8, atol=1e-8)
+    rows = {}
+    for lanes in (1, 4):
+        h = _handle("gyro", "Dopri5", y0, p, rtol=1e-8, atol=1e-8)
+        h.set_lanes_per_member(lanes)
+        h.set_output(grid, 0)                                # includes t0: the row of the initial state
+        h.set_schedule(32, np.random.RandomState(3).permutation(N).astype(np.intc))
+        h.simulate(0.04)
+        mid = h.get_dense()
+        assert np.isfinite(mid[grid <= 0.04]).all() and np.isnan(mid[grid > 0.04]).all()
+        h.simulate(0.1)                                      # continuation: the remaining rows
+        rows[lanes] = h.get_dense()
+        assert np.array_equal(rows[lanes][0], y0) and np.isfinite(rows[lanes]).all()
+        assert h.last_lanes_per_member() == lanes
+        # orthogonality of the rotation matrix and |pi| in every row (size-independent properties of the model)
+        Q = rows[lanes][:, :, 3:].reshape(len(grid), N, 3, 3)
+        assert np.max(np.abs(np.einsum("tnij,tnkj->tnik", Q, Q) - np.eye(3))) < 1e-6
+        h.close()
+    assert np.nanmax(np.abs(np.transpose(rows[4][1:], (1, 0, 2)) - o["dense"]) / np.maximum(np.abs(o["dense"]), 1.0)) <= 1e-6
+    assert rel_err(rows[4][:9], rows[1][:9]) <= 1e-10       # rows of the first call: the same steps in both kernels
+
+
+def test_split_kernel_selection_rules():
+    from assimulo_b200.gpu import Batched_Explicit_Problem, Dopri5, Radau5ODE, _core
+    y0, p = cases.gyro_sweep(64)
+    h = _handle("gyro", "Dopri5", y0, p, rtol=1e-8, atol=1e-8, arith=0)     # strict arithmetic: one thread per member
+    h.simulate(0.1)
+    assert h.last_lanes_per_member() == 1
+    h.set_lanes_per_member(4)
+    with pytest.raises(_core.AensError):
+        h.simulate(0.1)
+    h.close()
+    y0v, mu = cases.vdp_sweep(64)
+    h = _handle("vdp", "Dopri5", y0v, mu)
+    h.set_lanes_per_member(4)
+    with pytest.raises(_core.AensError):                                      # the model has no cooperative form
+        h.simulate(1.0)
+    h.close()
+    sim = Dopri5(Batched_Explicit_Problem(model="gyro", y0=y0, p0=p))
+    sim.rtol = sim.atol = 1e-8
+    sim.reduce_rows = True                                                    # row reduction: thread-per-member kernels
+    sim.simulate(0.1, 4)
+    assert sim._handle.last_lanes_per_member() == 1 and (sim.row_statistics["count"] == 64).all()
+    sim2 = Radau5ODE(Batched_Explicit_Problem(model="gyro", y0=y0, p0=p))
+    sim2.simulate(0.1)
+    assert sim2._handle.last_lanes_per_member() == 1 and (sim2.status == 0).all()

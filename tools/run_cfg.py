@@ -42,9 +42,11 @@ if which == "gyrored":
     h.set_row_reduction(True)
 h.set_output(grid, 16)
 h.set_fetch_reverse(rev)
+if os.environ.get("AENS_LANES"):
+    h.set_lanes_per_member(int(os.environ["AENS_LANES"]))
 for _ in range(reps):
     h.reset(); h.simulate(tf)
-    print(which, "kernel ms", h.last_kernel_ms(), h.get_summary())
+    print(which, "kernel ms", h.last_kernel_ms(), "lanes", h.last_lanes_per_member(), h.get_summary())
 if which == "gyrored":
     import time
     t0 = time.perf_counter(); rs = h.get_row_reduction(); t1 = time.perf_counter()
