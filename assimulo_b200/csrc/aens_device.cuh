@@ -246,6 +246,15 @@ AENS_DEV void seg_init_events(Lane<M> &L) {
 
 /* src/ode_event_locator.c:17-149 wrapped as in src/explicit_ode.pyx:332-361.  `S::interp(x, out)` is the dense
  * output of the step just taken.  On AENS_R_EVENT, t_high / y_high hold the event point. */
+/* bit i = (g[i] > 0): the locator's sign tests on one small mask per bracket end instead of on the doubles */
+template <int NG>
+AENS_DEV unsigned pos_mask(const double *g) {
+    unsigned m = 0;
+#pragma unroll
+    for (int i = 0; i < NG; ++i) m |= (is_pos(g[i]) ? 1u : 0u) << i;
+    return m;
+}
+
 template <class M, class S>
 AENS_DEV int aens_locate(S &s, Lane<M> &L, double t_low, double &t_high, double *y_high) {
     constexpr int NG = M::NG > 0 ? M::NG : 1;
@@ -255,35 +264,46 @@ AENS_DEV int aens_locate(S &s, Lane<M> &L, double t_low, double &t_high, double 
     const double TOL = dmax(dabs(t_low), dabs(t_high)) * 1.e-13;
     M::events(t_high, y_high, L.sw, L.p, g_high);
     L.st[AENS_STAT_NSTATEFCNS] += 1;
-    bool ev = false;
-#pragma unroll
-    for (int i = 0; i < M::NG; ++i) ev = ev || (is_pos(g_low[i]) != is_pos(g_high[i]));
+    /* detection (ode_event_locator.c:55): some (g_low > 0) != (g_high > 0) */
+    unsigned pm_low = pos_mask<M::NG>(g_low), pm_high = pos_mask<M::NG>(g_high);
+    const bool ev = (pm_low != pm_high);
     if (ev) {
         int side = 0, sideprev = -1;
         double alpha = 1.;
+        const double half_tol = TOL / 2.;
         while (dabs(t_high - t_low) > TOL) {
             if (side == sideprev) {
                 if (side == 2) alpha *= 2.; else alpha /= 2.;
             } else {
                 alpha = 1.;
             }
-            /* component with the largest |g_high/(g_low-g_high)| among the sign-changed ones (ties -> last) */
-            double maxfrac = 0., gh = g_high[0], gl = g_low[0];
+            /* component with the largest |g_high/(g_low-g_high)| among the sign-changed ones (ties -> last).  With a
+             * single sign change -- the usual case -- that component is the answer and the quotients are not needed
+             * (they only rank the candidates); the STRICT build keeps the reference's loop as it stands. */
+            const unsigned changed = pm_low ^ pm_high;
+            double gh = g_high[0], gl = g_low[0];
+            if (!AENS_STRICT && (changed & (changed - 1u)) == 0u) {
 #pragma unroll
-            for (int i = 0; i < M::NG; ++i) {
-                if (is_pos(g_low[i]) != is_pos(g_high[i])) {
-                    const double gfrac = dabs(r_div(g_high[i], g_low[i] - g_high[i]));
-                    if (gfrac >= maxfrac) { maxfrac = gfrac; gh = g_high[i]; gl = g_low[i]; }
+                for (int i = 1; i < M::NG; ++i)
+                    if ((changed >> i) & 1u) { gh = g_high[i]; gl = g_low[i]; }
+            } else {
+                double maxfrac = 0.;
+#pragma unroll
+                for (int i = 0; i < M::NG; ++i) {
+                    if ((changed >> i) & 1u) {
+                        const double gfrac = dabs(r_div(g_high[i], g_low[i] - g_high[i]));
+                        if (gfrac >= maxfrac) { maxfrac = gfrac; gh = g_high[i]; gl = g_low[i]; }
+                    }
                 }
             }
             double t_mid;
             if (gh == 0 || gl == 0) t_mid = (t_low + t_high) / 2.;
             else t_mid = t_high - r_div((t_high - t_low) * gh, gh - alpha * gl);
-            if (dabs(t_mid - t_low) < TOL / 2.) {
+            if (dabs(t_mid - t_low) < half_tol) {
                 const double fracint = r_div(dabs(t_low - t_high), TOL);
                 t_mid = t_low + r_div(t_high - t_low, 2. * dmin(fracint, 5.));
             }
-            if (dabs(t_mid - t_high) < TOL / 2.) {
+            if (dabs(t_mid - t_high) < half_tol) {
                 const double fracint = r_div(dabs(t_low - t_high), TOL);
                 t_mid = t_high - r_div(t_high - t_low, 2. * dmin(fracint, 5.));
             }
@@ -291,27 +311,26 @@ AENS_DEV int aens_locate(S &s, Lane<M> &L, double t_low, double &t_high, double 
             M::events(t_mid, y_high, L.sw, L.p, g_mid);
             L.st[AENS_STAT_NSTATEFCNS] += 1;
             sideprev = side;
-            bool left = false;
-#pragma unroll
-            for (int i = 0; i < M::NG; ++i) left = left || (is_pos(g_low[i]) != is_pos(g_mid[i]));
-            if (left) {
+            const unsigned pm_mid = pos_mask<M::NG>(g_mid);
+            if (pm_low != pm_mid) { /* an event in [t_low, t_mid] */
                 t_high = t_mid;
 #pragma unroll
                 for (int i = 0; i < M::NG; ++i) g_high[i] = g_mid[i];
+                pm_high = pm_mid;
                 side = 1;
             } else {
                 t_low = t_mid;
 #pragma unroll
                 for (int i = 0; i < M::NG; ++i) g_low[i] = g_mid[i];
+                pm_low = pm_mid;
                 side = 2;
             }
         }
         s.interp(t_high, y_high);
+        const unsigned changed = pm_low ^ pm_high;
 #pragma unroll
-        for (int i = 0; i < M::NG; ++i) {
-            L.event_info[i] = 0;
-            if (is_pos(g_low[i]) != is_pos(g_high[i])) L.event_info[i] = is_pos(g_high[i]) ? 1 : -1;
-        }
+        for (int i = 0; i < M::NG; ++i)
+            L.event_info[i] = ((changed >> i) & 1u) ? (((pm_high >> i) & 1u) ? 1 : -1) : 0;
         L.st[AENS_STAT_NSTATEEVENTS] += 1;
     }
 #pragma unroll

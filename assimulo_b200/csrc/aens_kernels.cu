@@ -30,8 +30,10 @@
 #ifndef AENS_MB_DOPRI5
 #define AENS_MB_DOPRI5 1
 #endif
+/* Radau5ODE / RodasODE on small systems: three CTAs per SM (<= 168 registers; the Jacobian, the collocation
+ * polynomial and f(x, y) live in shared memory, aens_radau5.cuh) -- 1.41 -> 1.18 ms on config 4, profiles/r2_radau.md */
 #ifndef AENS_MB_RADAU5
-#define AENS_MB_RADAU5 1
+#define AENS_MB_RADAU5 (AENS_KMODEL::N <= 4 ? 3 : 1)
 #endif
 
 typedef AENS_KMODEL KM;

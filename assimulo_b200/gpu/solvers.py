@@ -485,8 +485,8 @@ class Batched_Explicit_ODE(object):
             raise AssimuloException("lanes_per_member must be 0 (automatic), 1 or the model's group size.")
         self.options["lanes_per_member"] = v
     lanes_per_member = property(lambda self: self.options["lanes_per_member"], _set_lanes,
-                                doc="0: the library chooses between one thread per member and, for models that define "
-                                    "it (gyro: 4 lanes x 3 states), the sub-warp-per-member kernel; 1 / G force one.")
+                                doc="0 / 1: one thread per member (the default: it measured faster); G: the model's "
+                                    "sub-warp-per-member Dopri5 kernel where it defines one (gyro: 4 lanes x 3 states).")
 
     def _get_reduce_rows(self):
         """True: the rows of the output grid (ncp / ncp_list) are reduced over the ensemble inside the integration

@@ -256,8 +256,14 @@ def config_table():
         "cfg2_rk34": dict(title="cfg2 RungeKutta34 rtol=atol=1e-6", members=1 << 20, model="vdp", solver="RungeKutta34",
                           build=cases.vdp_sweep, tf=2.0, flops=30 * 2 + 5 * 5 + 12,
                           opts=dict(rtol=1e-6, atol=1e-6, inith=0.01), reverse=True),
+        # per accepted step 81n + 6F + 20 = 182 (n = 2, F = 0), plus the event locator's probes ("182 (+ event
+        # probes)"): every Illinois iteration of src/ode_event_locator.c:64-142 is one dense-output evaluation (8n + 3 =
+        # 19) and 14 flops of its own (bracket width, alpha, the secant formula, the two nudge tests).  Iterations =
+        # nstatefcns - one g per accepted step - two per segment (segment start + DOPRI5's first SOLOUT call).
         "cfg3": dict(title="cfg3 Dopri5 bouncing ball, state events on device", members=1 << 20, model="ball",
-                     solver="Dopri5", build=cases.ball_sweep, tf=3.0, flops=81 * 2 + 20, opts=dict(rtol=1e-6, atol=1e-6)),
+                     solver="Dopri5", build=cases.ball_sweep, tf=3.0, flops=81 * 2 + 20, opts=dict(rtol=1e-6, atol=1e-6),
+                     extra_flops=lambda sums, members: 33.0 * (sums["nstatefcns"] - sums["nsteps"]
+                                                               - 2 * (members + sums["nstateevents"]))),
         "cfg4": dict(title="cfg4 Radau5ODE Robertson, analytic Jacobian", members=1 << 18, model="robertson",
                      solver="Radau5ODE", build=cases.robertson_sweep, tf=40.0, flops=RADAU_ROBERTSON_FLOPS, opts=rob_opts),
         "cfg4_rodas": dict(title="cfg4' RodasODE Robertson, analytic Jacobian", members=1 << 18, model="robertson",
@@ -314,6 +320,8 @@ def run_config(device, cfg, rank, world, peak_tflops, hbm_gbs, steps=3, warmup=1
     sums, nbad = h.get_summary()
     n = y0.shape[1]
     flops = cfg["flops"]
+    if cfg.get("extra_flops"):  # work the solver does besides its steps (event location), spread over the accepted steps
+        flops = flops + cfg["extra_flops"](sums, int(y0.shape[0])) / max(int(sums["nsteps"]), 1)
     rec = {"name": cfg["title"], "members": int(y0.shape[0]), "model": cfg["model"], "solver": cfg["solver"],
            "kernel_ms": ms, "stat": "mean of %d launches after %d warm-up" % (steps, warmup),
            "kernel_ms_min": float(min(ms_all)), "accepted_steps": int(sums["nsteps"]),

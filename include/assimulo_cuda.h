@@ -169,9 +169,10 @@ int aens_set_schedule(aens_handle_t *h, int refill_threshold, const int *order);
 /* Lanes per member.  The kernels integrate one member per thread; models with a larger state that define the
  * cooperative form of their right-hand side (built-in: "gyro", 4 lanes x 3 components) also have a
  * sub-warp-per-member Dopri5 kernel that keeps a quarter of the state in each lane's registers (csrc/aens_split.cuh).
- * lanes = 0 (default): the library picks -- the cooperative kernel where one exists and applies (FAST arithmetic,
- * no row reduction, not the one-call host modes); 1: always one thread per member; > 1: that many lanes or
- * AENS_ERR_UNSUPPORTED.  aens_last_lanes_per_member reports what the most recent launch used. */
+ * lanes = 0 (default): the library picks -- one thread per member, which measured faster on the gyroscope ensemble
+ * (profiles/r2_split.md); 1: always one thread per member; > 1: that many lanes (FAST arithmetic, no row reduction,
+ * not the one-call host modes) or AENS_ERR_UNSUPPORTED.  aens_last_lanes_per_member reports what the most recent
+ * launch used. */
 int aens_set_lanes_per_member(aens_handle_t *h, int lanes);
 int aens_last_lanes_per_member(const aens_handle_t *h);
 

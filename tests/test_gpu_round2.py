@@ -331,7 +331,7 @@ def test_split_dopri5_gyro_matches_oracle_and_thread_per_member(N):
         h = _handle("gyro", "Dopri5", y0, p, rtol=1e-8, atol=1e-8)
         h.set_lanes_per_member(lanes)
         h.simulate(0.1)
-        assert h.last_lanes_per_member() == (1 if lanes == 1 else 4)      # automatic = the cooperative kernel
+        assert h.last_lanes_per_member() == (4 if lanes == 4 else 1)      # automatic = one thread per member (the faster one)
         t, y, _, st = h.get_final()
         res[lanes] = (y, h.get_stats("nsteps"), h.get_stats("nfcns"), h.get_stats("nerrfails"))
         assert (st == 0).all() and (t == 0.1).all()
@@ -340,7 +340,7 @@ def test_split_dopri5_gyro_matches_oracle_and_thread_per_member(N):
         h.close()
     # same arithmetic per component, only the summation order of the norms differs: the two kernels agree far below rtol
     assert rel_err(res[4][0], res[1][0]) <= 1e-10
-    assert np.array_equal(res[0][0], res[4][0])
+    assert np.array_equal(res[0][0], res[1][0])
 
 
 def test_split_dopri5_gyro_dense_rows_order_and_continuation():
