@@ -555,7 +555,7 @@ AENS_DEV int aens_post_step(S &s, Lane<M> &L, const aens_args_t &a, long long id
 /* ------------------------------------------------------------------------------------------------------- */
 /* small dense LU of aens_radau5.cuh (Moler's DEC/SOL = LAPACK's partial pivoting) */
 template <int N> AENS_DEV int lu_dec(double *a, int *ip);
-template <int N> AENS_DEV void lu_sol(const double *a, double *b, const int *ip);
+template <int N, bool PIV = true> AENS_DEV void lu_sol(const double *a, double *b, const int *ip);
 
 template <class M, int DENSE, bool IMPL = false>
 struct Euler {

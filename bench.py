@@ -575,6 +575,7 @@ def main_gpu(a, rank, world, local_rank):
     # integration of the same members on rank 0 (bit-identical: members do not interact) ----
     gather_check = None
     if world > 1:
+        sim._handle.allgather_results(GATHER_WHAT | _core.GATHER_STATS)   # (the timed steps gather {t, y, status} only)
         g = sim._handle.get_gathered(n_total, want_stats=True)
         if rank == 0:
             S = 4096
