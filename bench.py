@@ -360,9 +360,20 @@ def main_config(a, rank, world, local_rank):
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    cfg = config_table()[a.config]
     peak_tflops, _ = _core.measure_fp64_peak(local_rank, 0.5)
     hbm = measured_hbm()
+    names = list(config_table()) if a.config == "all" else [a.config]
+    for name in names:      # "all": one JSON line per configuration, one process group for all of them
+        cfg = config_table()[name]
+        _config_line(a, cfg, rank, world, local_rank, peak_tflops, hbm, json_fd)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def _config_line(a, cfg, rank, world, local_rank, peak_tflops, hbm, json_fd):
+    import torch
+    import torch.distributed as dist
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
@@ -391,9 +402,6 @@ def main_config(a, rank, world, local_rank):
                               "frac": rec["accepted_steps"] * rec["flops_per_accepted_step"] / (ms * 1e-3) / 1e12 / peak_tflops,
                               "traffic": None, "flops_per_accepted_step": rec["flops_per_accepted_step"]})}
         os.write(json_fd, (json.dumps(line) + "\n").encode())
-    if world > 1:
-        dist.destroy_process_group()
-    return 0
 
 
 def measured_hbm():
@@ -702,7 +710,7 @@ def main():
                     help="skip the BASELINE.json configs 2-5 inside the headline line (N = 1 only)")
     ap.add_argument("--config", default="headline",
                     help="headline (default) or one of the other BASELINE configurations as the timed workload, at any "
-                         "--gpus: cfg2_rk4 cfg2_rk34 cfg3 cfg4 cfg4_rodas cfg5 cfg5_reduced")
+                         "--gpus: cfg2_rk4 cfg2_rk34 cfg3 cfg4 cfg4_rodas cfg5 cfg5_reduced, or all (one line each)")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3) if a.impl == "graft" else a.warmup
     rank = int(os.environ.get("RANK", "0"))
