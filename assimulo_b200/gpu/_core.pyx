@@ -91,6 +91,7 @@ cdef extern from "assimulo_cuda.h":
     int aens_comm_init(aens_handle_t *h, int rank, int nranks, const void *id128) nogil
     int aens_comm_destroy(aens_handle_t *h) nogil
     int aens_allgather_results(aens_handle_t *h, int what) nogil
+    int aens_set_gather_in_simulate(aens_handle_t *h, int what) nogil
     int aens_last_gather_ms(aens_handle_t *h, float *ms) nogil
     int aens_gathered_ptr(aens_handle_t *h, void **ptr, long long *rec_bytes, int *nranks) nogil
     int aens_get_gathered(aens_handle_t *h, long long n_total, double *t, double *y, int *status, int *stats,
@@ -412,6 +413,10 @@ cdef class Handle:
         with nogil:
             rc = aens_allgather_results(self.h, what)
         self._check(rc)
+
+    def set_gather_in_simulate(self, int what):
+        """what != 0: every simulate ends with the all-gather of these fields, issued right behind the last kernel."""
+        self._check(aens_set_gather_in_simulate(self.h, what))
 
     def last_gather_ms(self):
         cdef float ms = 0

@@ -73,6 +73,15 @@ def comm_init(solver, group=None):
     solver._comm_ready = id(solver._handle)
 
 
+def gather_in_simulate(solver, what, group=None):
+    """Make every simulate() of `solver` end with the all-gather of the fields `what` (a mask of _core.GATHER_*; 0 = off),
+    issued by the library right behind the last integration kernel (aens_set_gather_in_simulate): with the chunked host
+    modes the exchange over NVLink overlaps the device->host copies of the last chunks over PCIe."""
+    if what:
+        comm_init(solver, group)
+    solver._get_handle().set_gather_in_simulate(int(what))
+
+
 def allgather_device(solver, what=0):
     """ONE ncclAllGather of this rank's packed final results, issued by the library on the handle's stream
     (aens_allgather_results; asynchronous).  The gathered records stay on the device (handle.gathered_ptr());

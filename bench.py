@@ -522,11 +522,8 @@ def main_gpu(a, rank, world, local_rank):
         def step():
             sm.reset()                    # back to (t0, y0): the next simulate() uploads the inputs again
             sm.simulate(TF)               # H2D inputs / kernel(s) / D2H final states + summary, mode = sm.host_mode
-            assert sm.n_not_complete == 0
-            if world > 1:
-                parallel.allgather_device(sm, GATHER_WHAT)
-                sm._handle.sync()
-            return sm.statistics["nsteps"]
+            assert sm.n_not_complete == 0                 # at N > 1 the library issued the all-gather behind the last
+            return sm.statistics["nsteps"]                # kernel (gather_in_simulate) and simulate() waited for it
         return step
 
     def time_steps(step, k):
@@ -560,18 +557,27 @@ def main_gpu(a, rank, world, local_rank):
     assert prob.y0_row is not None
     sim = make_sim(prob)
     if world > 1:
-        parallel.comm_init(sim)
+        parallel.gather_in_simulate(sim, GATHER_WHAT)
     e2e_step = make_step(sim)
     e2e_mode, e2e_modes = tune(sim, e2e_step)
     for _ in range(max(1, a.warmup // 2)):
         e2e_step()
     e2e_wall, e2e_steps = time_steps(e2e_step, a.steps)
-    gather_ms = sim._handle.last_gather_ms() if world > 1 else 0.0
+    gather_ms = sim._handle.last_gather_ms() if world > 1 else 0.0      # inside the step: includes waiting for the last rank
+    gather_alone_ms = 0.0
+    if world > 1:   # the exchange by itself, all ranks ready: what it costs when nothing hides it
+        ga = []
+        for _ in range(3):
+            barrier()
+            sim._handle.allgather_results(GATHER_WHAT)
+            sim._handle.sync()
+            ga.append(sim._handle.last_gather_ms())
+        gather_alone_ms = float(np.median(ga))
     # the general case: every member with its own initial state (y0[N, 2] uploaded every step); extra key
     prob2 = Batched_Explicit_Problem(model="vdp", y0=y0_h, p0=p_h, detect_shared_y0=False)
     sim2 = make_sim(prob2)
     if world > 1:
-        parallel.comm_init(sim2)
+        parallel.gather_in_simulate(sim2, GATHER_WHAT)
     e2e2_step = make_step(sim2)
     e2e2_mode, e2e2_modes = tune(sim2, e2e2_step)
     e2e2_wall, e2e2_steps = time_steps(e2e2_step, a.steps)
@@ -611,13 +617,13 @@ def main_gpu(a, rank, world, local_rank):
         del g
 
     # ---- reduce over ranks: MAX time, SUM work ----
-    vals = torch.tensor([total_ms, e2e_wall, float(np.mean(kernel_ms)), e2e2_wall, gather_ms], dtype=torch.float64,
-                        device="cuda")
+    vals = torch.tensor([total_ms, e2e_wall, float(np.mean(kernel_ms)), e2e2_wall, gather_ms, gather_alone_ms],
+                        dtype=torch.float64, device="cuda")
     work = torch.tensor([float(steps_rank), float(e2e_steps), float(e2e2_steps)], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(vals, op=dist.ReduceOp.MAX)
         dist.all_reduce(work, op=dist.ReduceOp.SUM)
-    total_ms, e2e_wall, kern_ms, e2e2_wall, gather_ms = [float(v) for v in vals.cpu()]
+    total_ms, e2e_wall, kern_ms, e2e2_wall, gather_ms, gather_alone_ms = [float(v) for v in vals.cpu()]
     steps_all, e2e_steps_all, e2e2_steps_all = [float(v) for v in work.cpu()]
 
     if rank == 0:
@@ -627,14 +633,15 @@ def main_gpu(a, rank, world, local_rank):
         nominal = 148 * 64 * 2 * 1.965e9 / 1e12
 
         def floor(h2d_b, d2h_b):
-            """lower bound of one e2e step on this box: the kernel, or the step's bytes at the best rate each direction
-            of the host link sustained with all ranks busy (copy engine or SM-initiated, per-GPU minimum), whichever
-            is longer; plus the all-gather, which follows the kernel"""
+            """lower bound of one e2e step on this box: the kernel followed by the all-gather (the exchange needs the
+            results in HBM), or the step's bytes at the best rate each direction of the host link sustained with all
+            ranks busy (copy engine or SM-initiated; the slowest GPU's link, since the step ends when the last rank is
+            done), whichever is longer"""
             up = max(link_min[0], link_min[3])
             down = max(link_min[1], link_min[4])
             link_ms = max(h2d_b / up, d2h_b / down) / 1e6
-            return {"kernel_ms": kern_ms, "link_ms": link_ms, "gather_ms": gather_ms,
-                    "floor_ms": max(kern_ms, link_ms) + gather_ms}
+            return {"kernel_ms": kern_ms, "link_ms": link_ms, "gather_alone_ms": gather_alone_ms,
+                    "floor_ms": max(kern_ms + gather_alone_ms, link_ms)}
         f1, f2 = floor(h2d, d2h), floor(h2d2, d2h)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
@@ -643,7 +650,8 @@ def main_gpu(a, rank, world, local_rank):
             "accepted_steps_per_pass": steps_all, "kernel_ms": kern_ms,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": e2e_wall / a.steps * 1e3, "host_mode": e2e_mode, "host_mode_probe_ms": e2e_modes,
-                    "gather_ms": gather_ms, "gather_bytes_per_rank": int(N * 28 + 32) if world > 1 else 0,
+                    "gather_ms": gather_ms, "gather_alone_ms": gather_alone_ms,
+                    "gather_bytes_per_rank": int(N * 28 + 32) if world > 1 else 0,
                     "floor": f1, "frac_of_floor": f1["floor_ms"] / (e2e_wall / a.steps * 1e3),
                     "path": "Dopri5(Batched_Explicit_Problem(y0[N,2], mu[N])).simulate() -> aens_simulate_host through "
                             "the C ABI with pinned HOST arrays; the problem class detects that all y0 rows are equal, so "

@@ -296,6 +296,11 @@ int aens_comm_unique_id(void *id128);
 int aens_comm_init(aens_handle_t *h, int rank, int nranks, const void *id128);
 int aens_comm_destroy(aens_handle_t *h);
 int aens_allgather_results(aens_handle_t *h, int what);
+/* what != 0: every aens_simulate / aens_simulate_async / aens_simulate_host on a handle with a communicator ends with
+ * aens_allgather_results(h, what), issued by the library at the earliest point -- right behind the last integration
+ * kernel.  In the chunked host modes the exchange then runs over NVLink while the copy engines are still moving the
+ * last chunks' results to the host over PCIe (the two do not share a link).  0 switches it off (default). */
+int aens_set_gather_in_simulate(aens_handle_t *h, int what);
 int aens_last_gather_ms(aens_handle_t *h, float *ms);
 int aens_gathered_ptr(aens_handle_t *h, void **ptr, long long *rec_bytes, int *nranks);
 int aens_get_gathered(aens_handle_t *h, long long n_total, double *t, double *y, int *status, int *stats,

@@ -164,7 +164,13 @@ def test_ball_events(solver, opts, arith):
     if arith == "strict":
         for k in ("nsteps", "nfcns"):
             assert np.array_equal(g["stats"][k], o["stats"][k]), k
-        # the number of locator probes may differ by a few where a 1-ulp difference changes a secant iterate
+        # The locator itself is reproduced operation for operation: with the fixed-step solver, whose step sizes involve
+        # no library function, every member makes exactly the oracle's probes.  The adaptive solvers size their steps
+        # with pow() (HINIT's fifth root, the controller's err^expo1 / facold^beta), where the device library and glibc
+        # differ by an ulp now and then; such a step ends an ulp away, the secant iterates shift with it and an
+        # iteration more or less meets the 1e-13 bracket -- a few probes per thousand, never an event.
+        if solver == "ExplicitEuler":
+            assert np.array_equal(g["stats"]["nstatefcns"], o["stats"]["nstatefcns"])
         assert abs(int(g["stats"]["nstatefcns"].sum()) - int(o["stats"]["nstatefcns"].sum())) <= 0.02 * o["stats"]["nstatefcns"].sum()
         assert np.max(np.abs(g["ev_t"][m] - o["ev_t"][m])) <= 2e-12
     # first impact against the closed form t = sqrt(2 h0 / g)
@@ -255,8 +261,8 @@ def test_radau5_stiff_vdp_reference_case():
 
 @pytest.mark.parametrize("arith", ["strict", "fast"])
 def test_gyro_dense_output(arith):
-    N = 1024
-    y0, p = cases.gyro_sweep(1 << 22, np.arange(0, 1 << 22, 4096))
+    N = 4096                                                          # every 1024th member of config 5
+    y0, p = cases.gyro_sweep(1 << 22, np.arange(0, 1 << 22, 1024))
     grid = np.linspace(0.0, 0.1, 101)[1:]
     o = O.simulate("gyro", "Dopri5", y0, p, tf=0.1, t_grid=grid, rtol=1e-8, atol=1e-8)
     g = gpu("gyro", "Dopri5", y0, p, tf=0.1, t_grid=grid, arith=arith, rtol=1e-8, atol=1e-8)

@@ -290,10 +290,33 @@ def test_allgather_single_rank_communicator_packs_and_unpacks():
     assert np.array_equal(g2["y"], y[:100]) and np.array_equal(g2["status"], st[:100])
     with pytest.raises(_core.AensError):
         h.get_gathered(100, want_t=True, want_stats=False)          # t was not part of that gather
+    # the library issues the exchange itself, right behind the last kernel of every simulate
+    h.set_gather_in_simulate(_core.GATHER_T | _core.GATHER_Y)
+    h.reset()
+    h.simulate(1.5)
+    g3 = h.get_gathered(N, want_status=False, want_stats=False)
+    t3, y3, _, _ = h.get_final()
+    assert np.array_equal(g3["y"], y3) and np.array_equal(g3["t"], t3) and not np.array_equal(y3, y)
+    h.set_gather_in_simulate(0)
     h.comm_destroy()
     with pytest.raises(_core.AensError):
         h.allgather_results(0)
     h.close()
+    # ... also in the one-call host modes (chunked: the exchange overlaps the device->host copies of the last chunks)
+    y0v, mu = cases.vdp_sweep(N)
+    for mode in (1, 2, 3):
+        hv = _core.Handle(0)
+        hv.set_model_builtin("vdp")
+        hv.set_opts({"solver": _core.SOLVER_IDS["Dopri5"]})
+        hv.set_host_mode(mode)
+        hv.comm_init(0, 1, _core.comm_unique_id())
+        hv.set_gather_in_simulate(_core.GATHER_Y | _core.GATHER_STATUS)
+        y0_h, p_h, out = _core.pinned_empty((N, 2)), _core.pinned_empty((N, 1)), _core.pinned_empty((N, 2))
+        y0_h[:], p_h[:] = y0v, mu
+        hv.simulate_host(y0_h, p_h, None, 0.0, 2.0, out_y=out, nchunks=4)
+        gv = hv.get_gathered(N, want_t=False, want_stats=False)
+        assert np.array_equal(gv["y"], out) and (gv["status"] == 0).all()
+        hv.close()
 
 
 def test_allgather_over_nccl_on_two_gpus():
