@@ -170,7 +170,7 @@ struct Lane {
             } else {
                 load_row<M::N>(a.in_y, idx, y);
             }
-            t = a.t0;
+            t = a.t0; /* (the host passes -t0 to the time-reversed kernels) */
 #pragma unroll
             for (int i = 0; i < M::N; ++i) a.y0_store[(long long)i * a.N + idx] = y[i];
             if (M::NP > 0) {
@@ -185,7 +185,7 @@ struct Lane {
             }
             gi = 0;
         } else {
-            t = a.t[idx];
+            t = M::REV ? -a.t[idx] : a.t[idx]; /* memory holds t, a time-reversed kernel works in s = -t */
 #pragma unroll
             for (int i = 0; i < M::N; ++i) y[i] = a.y[(long long)i * a.N + idx];
 #pragma unroll
@@ -215,7 +215,7 @@ struct Lane {
                 }
             }
         }
-        a.t[idx] = t;
+        a.t[idx] = M::REV ? -t : t;
 #pragma unroll
         for (int i = 0; i < M::N; ++i) a.y[(long long)i * a.N + idx] = y[i];
 #pragma unroll
@@ -225,7 +225,7 @@ struct Lane {
         if (a.n_grid > 0) a.grid_idx[idx] = gi;
         a.status[idx] = status;
         if (a.out_y) store_row<M::N>(a.out_y, idx, y);
-        if (a.out_t) a.out_t[idx] = t;
+        if (a.out_t) a.out_t[idx] = M::REV ? -t : t;
         if (a.out_status) a.out_status[idx] = status;
         if (M::NSW > 0 && a.out_sw) {
 #pragma unroll
@@ -1513,7 +1513,7 @@ __device__ __forceinline__ void aens_run(const aens_args_t &a) {
                             if (s.L.event_info[i] != 0)
                                 mask |= (1 << (2 * i)) | ((s.L.event_info[i] > 0 ? 1 : 0) << (2 * i + 1));
                         const long long slot = (long long)(ne % a.ev_slots) * a.N + idx;
-                        a.ev_t[slot] = s.L.t;
+                        a.ev_t[slot] = M::REV ? -s.L.t : s.L.t;
                         a.ev_info[slot] = mask;
                     }
                     const int term = M::handle_event(s.L.t, s.L.y, s.L.sw, s.L.event_info, s.L.p);

@@ -60,6 +60,20 @@ AENS_DEFINE_KERNEL(KN(aens_dopri5_d0_), Dopri5, KM, kEvents, AENS_MB_DOPRI5)
 AENS_DEFINE_KERNEL(KN(aens_radau5_d0_), Radau5, KM, kEvents, AENS_MB_RADAU5)
 AENS_DEFINE_KERNEL(KN(aens_impleuler_d0_), ImplEuler, KM, kEvents, AENS_MB_EULER)
 
+/* backward integration: the three solvers whose reference cores carry POSNEG, on the time-reversed model */
+typedef AensRev<KM> KMR;
+AENS_DEFINE_KERNEL(KN(aens_dopri5_b1_), Dopri5, KMR, true, AENS_MB_DOPRI5)
+AENS_DEFINE_KERNEL(KN(aens_radau5_b1_), Radau5, KMR, true, AENS_MB_RADAU5)
+AENS_DEFINE_KERNEL(KN(aens_rodas_b1_), Rodas, KMR, true, AENS_MB_RADAU5)
+extern "C" const void *AENS_CAT(AENS_CAT(aens_kernels_bwd_, AENS_KNAME), AENS_SUF)(int solver) {
+    switch (solver) {
+    case AENS_SOLVER_DOPRI5: return (const void *)KN(aens_dopri5_b1_);
+    case AENS_SOLVER_RADAU5: return (const void *)KN(aens_radau5_b1_);
+    case AENS_SOLVER_RODAS: return (const void *)KN(aens_rodas_b1_);
+    }
+    return nullptr;
+}
+
 /* sub-warp-per-member Dopri5 (aens_split.cuh) for the models that define rhs_g; FAST build only */
 #ifndef AENS_MB_SPLIT
 #define AENS_MB_SPLIT 1

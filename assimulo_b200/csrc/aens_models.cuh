@@ -39,6 +39,8 @@ struct AensModelDefaults {
      * comp(j, c) = state index of component c of lane j, rhs_g() = this lane's part of f, fetching what it needs from
      * the other lanes of its group with warp shuffles.  G = 1: the model has no such form. */
     static constexpr int G = 1, NL = 0;
+    /* true only for AensRev<M>: the kernel's time axis is s = -t (backward integration) */
+    static constexpr bool REV = false;
     static AENS_DEV void prep(double *) {}
     static AENS_DEV double time_events(double, const double *, const unsigned char *, const double *) {
         return AENS_NO_TIME_EVENT;
@@ -233,6 +235,38 @@ struct AensTimeEv : AensModelDefaults {
     static AENS_DEV int handle_time_event(double, double *y, unsigned char *, const double *p) {
         y[0] += p[4];
         return 0;
+    }
+};
+
+/* Backward integration (options["backward"], src/explicit_ode.pyx:185,209,312).  The reference's cores integrate
+ * towards a smaller tfinal by carrying the sign of the direction through the step size (POSNEG: dopri5.f:380,
+ * radau5.c:341, rodas_decsol.f:569).  Here the same integration runs FORWARD in s = -t on the time-reversed problem
+ *     dy/ds = -f(-s, y),   g(-s, y),   J_s = -J
+ * with the unchanged steppers.  IEEE arithmetic is symmetric under a sign change of its operands, so every intermediate
+ * of the reversed run is the exact mirror image of the reference's (x + c h -> -(x + c h), h k -> h k), and the states,
+ * step counts and event times come out identical; only RODAS's df/dt forward difference looks at the other side of x.
+ * The host hands the kernel -tfinal and the negated output grid; Lane::load / store and the event log flip the sign of
+ * the times they move between the member's registers and memory (M::REV). */
+template <class M>
+struct AensRev : M {
+    static constexpr bool REV = true;
+    static constexpr bool HAS_RHS_H = false;
+    static constexpr int G = 1;
+    static AENS_DEV void rhs(double s, const double *y, const unsigned char *sw, const double *p, double *yd) {
+        M::rhs(-s, y, sw, p, yd);
+#pragma unroll
+        for (int i = 0; i < M::N; ++i) yd[i] = -yd[i];
+    }
+    static AENS_DEV void jac(double s, const double *y, const unsigned char *sw, const double *p, double *J) {
+        M::jac(-s, y, sw, p, J);
+#pragma unroll(M::N <= 4 ? 64 : 1)
+        for (int i = 0; i < M::N * M::N; ++i) J[i] = -J[i];
+    }
+    static AENS_DEV void events(double s, const double *y, const unsigned char *sw, const double *p, double *g) {
+        M::events(-s, y, sw, p, g);
+    }
+    static AENS_DEV int handle_event(double s, double *y, unsigned char *sw, const int *info, const double *p) {
+        return M::handle_event(-s, y, sw, info, p);
     }
 };
 

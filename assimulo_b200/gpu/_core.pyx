@@ -85,6 +85,7 @@ cdef extern from "assimulo_cuda.h":
     int aens_get_row_reduction(aens_handle_t *h, double *mean, double *var, double *mn, double *mx,
                                long long *count) nogil
     int aens_set_time_limit(aens_handle_t *h, double seconds) nogil
+    int aens_set_backward(aens_handle_t *h, int on) nogil
     int aens_set_lanes_per_member(aens_handle_t *h, int lanes) nogil
     int aens_last_lanes_per_member(const aens_handle_t *h) nogil
     int aens_comm_unique_id(void *id128) nogil
@@ -388,6 +389,10 @@ cdef class Handle:
 
     def last_lanes_per_member(self):
         return aens_last_lanes_per_member(self.h)
+
+    def set_backward(self, on):
+        """options["backward"]: the next simulate() integrates from the members' current time down to tfinal."""
+        self._check(aens_set_backward(self.h, 1 if on else 0))
 
     def set_time_limit(self, double seconds):
         """ODE.time_limit: members a warp fetches later than `seconds` after the launch started are not integrated

@@ -58,6 +58,8 @@ class Batched_Explicit_ODE(object):
     """Base class: the batched counterpart of Explicit_ODE (src/explicit_ode.pyx:69-135) + ODE (src/ode.pyx)."""
     _solver_name = None
     _exc = Explicit_ODE_Exception
+    #: the reference's core of this solver carries the direction of integration (POSNEG)
+    _supports_backward = False
 
     def __init__(self, problem, device=None, comm=None):
         if not isinstance(problem, Batched_Explicit_Problem):
@@ -176,9 +178,14 @@ class Batched_Explicit_ODE(object):
             tfinal = float(tfinal)
         except (ValueError, TypeError):
             raise AssimuloException("Final time must be an integer or float.")
-        if self.t > tfinal:
+        backward = bool(self.options["backward"])
+        if self.t > tfinal and not backward:
             raise AssimuloException("Final time {} must be greater than start time {}.\n Perhaps you should consider "
-                                    "to reset the integration.".format(tfinal, self.t))
+                                    "to reset the integration. If the intention is to integrate backwards, please use "
+                                    "the backwards option.".format(tfinal, self.t))
+        if backward and self.t < tfinal:
+            raise AssimuloException("Final time {} must be smaller than start time {} when integrating "
+                                    "backwards.".format(tfinal, self.t))
         if not isinstance(ncp, int):
             raise AssimuloException("Number of communication points must be an integer")
         if ncp < 0:
@@ -187,6 +194,11 @@ class Batched_Explicit_ODE(object):
             ncp, ncp_list = 0, None  # e.g. RungeKutta4 (src/ode.pyx:260-263)
         if ncp != 0:
             output_list = np.linspace(t0, tfinal, ncp + 1)[1:]
+        elif ncp_list is not None and backward:   # src/ode.pyx:277-281
+            nl = np.array(ncp_list, dtype=float, ndmin=1)
+            output_list = -np.sort(-nl[np.logical_and(nl < t0, nl >= tfinal)])
+            if len(output_list) == 0 or output_list[-1] > tfinal:
+                output_list = np.append(output_list, tfinal)
         elif ncp_list is not None:
             nl = np.array(ncp_list, dtype=float, ndmin=1)
             output_list = nl[np.logical_and(nl > t0, nl <= tfinal)]
@@ -210,6 +222,7 @@ class Batched_Explicit_ODE(object):
         h.set_opts(self._opts_dict())
         h.set_time_limit(float(self.options["time_limit"] or 0.0))
         h.set_lanes_per_member(int(self.options["lanes_per_member"]))
+        h.set_backward(backward)
         h.set_host_mode(HOST_MODES[self.options["host_mode"]])
         pin = None
         if self.options["reuse_buffers"]:
@@ -221,7 +234,7 @@ class Batched_Explicit_ODE(object):
                              c.pinned_empty((self.N,), np.intc))
             pin = self._pin
         self.problem.handle_result(self, t0, self.y)
-        if self._dirty and output_list is None and order is None:
+        if self._dirty and output_list is None and order is None and not backward:
             # host -> device -> host in one chunk-pipelined call (aens_simulate_host): uploads, kernels and
             # downloads of consecutive member ranges overlap.  Only y comes back eagerly; the per-member end times
             # and status codes are fetched on first access -- the summary says whether any member did not complete.
@@ -297,7 +310,7 @@ class Batched_Explicit_ODE(object):
         else:
             self.problem.handle_result(self, tfinal, self.y)
         # the ensemble's current time: members that failed or were terminated stopped early (see status)
-        self.t = tfinal if nbad == 0 else float(np.min(self.t_members))
+        self.t = tfinal if nbad == 0 else float(np.max(self.t_members) if backward else np.min(self.t_members))
         self.finalize()
         self.problem.finalize(self)
         if nbad and self.options["time_limit"] and (self.status == ST_TIME_LIMIT).any():
@@ -422,10 +435,17 @@ class Batched_Explicit_ODE(object):
     clock_step = property(lambda self: self.options["clock_step"], _set_clock_step)
 
     def _set_backward(self, v):
-        if bool(v):
-            raise AssimuloException("Backward integration is not available in the batched solvers.")
-        self.options["backward"] = False
-    backward = property(lambda self: self.options["backward"], _set_backward)
+        if bool(v) and not self._supports_backward:
+            raise AssimuloException("Backward integration is available with Dopri5, Radau5ODE and RodasODE: %s has no "
+                                    "notion of direction in the reference either (its step size is never signed)."
+                                    % self._solver_name)
+        if bool(v) and (self.problem.time_events or self.options["reduce_rows"]):
+            raise AssimuloException("Backward integration is not available with time events or reduce_rows.")
+        self.options["backward"] = bool(v)
+    backward = property(lambda self: self.options["backward"], _set_backward,
+                        doc="Integrate from the current time DOWN to tfinal (src/ode.pyx:490-507).  The device "
+                            "integrates the time-reversed problem forward, which reproduces the reference's POSNEG "
+                            "integration value for value.")
 
     # ---- options shared by all batched solvers ------------------------------------------------------
     def _get_arith(self):
@@ -660,6 +680,7 @@ class Dopri5(Batched_Explicit_ODE):
     """Dormand-Prince 5(4) with Hairer's step-size control and dense output
     (src/solvers/runge_kutta.py:26-428 over thirdparty/hairer/dopri5.f)."""
     _solver_name = "Dopri5"
+    _supports_backward = True
     _exc = Dopri5_Exception
 
     def __init__(self, problem, **kw):
@@ -696,6 +717,7 @@ class Radau5ODE(Batched_Explicit_ODE):
     """Radau IIA(5), 3 stages, simplified Newton with per-member dense LU
     (src/solvers/radau5.py:69-430, src/lib/radau_core.py, core thirdparty/radau5/radau5.c)."""
     _solver_name = "Radau5ODE"
+    _supports_backward = True
     _exc = Radau_Exception
 
     def __init__(self, problem, **kw):
@@ -766,6 +788,7 @@ class RodasODE(Batched_Explicit_ODE):
     (src/solvers/rosenbrock.py:259-465 over thirdparty/hairer/rodas_decsol.f).  One LU decomposition per attempt,
     six stages, no Newton iteration; analytic or finite-difference Jacobian, df/dt by a forward difference."""
     _solver_name = "RodasODE"
+    _supports_backward = True
     _exc = Rodas_Exception
 
     def __init__(self, problem, **kw):

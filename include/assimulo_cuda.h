@@ -182,6 +182,14 @@ int aens_last_lanes_per_member(const aens_handle_t *h);
  * zero-copy host mode, where it evens out the rate at which inputs are pulled over PCIe. */
 int aens_set_fetch_reverse(aens_handle_t *h, int reverse);
 
+/* Backward integration (the reference's options["backward"], src/ode.pyx:490-507, src/explicit_ode.pyx:185,209,312):
+ * with on != 0 aens_simulate integrates every member from its current time DOWN to tfinal (tfinal <= t) and the output
+ * grid is descending.  Available with the three solvers whose reference cores carry the direction of integration --
+ * Dopri5, Radau5ODE, RodasODE (POSNEG: dopri5.f:380, radau5.c:341, rodas_decsol.f:569) --, state events included; not
+ * with time events, row reduction or aens_simulate_host.  The kernels integrate the time-reversed problem forward
+ * (csrc/aens_models.cuh AensRev), which reproduces the reference's backward run value for value. */
+int aens_set_backward(aens_handle_t *h, int on);
+
 /* Integrates every member from its current time to tfinal (continuation semantics of ODE.simulate,
  * src/ode.pyx:195-196,222).  Synchronous.  Returns AENS_OK even if individual members failed: see status[]. */
 int aens_simulate(aens_handle_t *h, double tfinal);

@@ -417,3 +417,89 @@ def test_split_kernel_selection_rules():
     sim2 = Radau5ODE(Batched_Explicit_Problem(model="gyro", y0=y0, p0=p))
     sim2.simulate(0.1)
     assert sim2._handle.last_lanes_per_member() == 1 and (sim2.status == 0).all()
+
+
+# ---------------------------------------------------------------------------------------------------------
+# backward integration (options["backward"]; POSNEG in dopri5.f:380, radau5.c:341, rodas_decsol.f:569)
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("solver", ["Dopri5", "Radau5ODE", "RodasODE"])
+def test_backward_integration_matches_oracle_and_reference_golden(solver):
+    import assimulo_b200.gpu as G
+    from conftest import golden
+    cls = getattr(G, solver)
+    g = golden("bwd_vdp_" + solver.lower())
+    N = len(g["mu"])
+    y0, mu = np.tile(g["y_start"], (N, 1)), g["mu"].reshape(-1, 1)
+    for arith in ("strict", "fast"):
+        sim = cls(G.Batched_Explicit_Problem(model="vdp", y0=y0, p0=mu, t0=2.0))
+        sim.arith, sim.backward = arith, True
+        sim.rtol = sim.atol = 1e-6
+        t, y = sim.simulate(0.0, 8)
+        assert np.allclose(t, g["t_rows"]) and sim.t == 0.0 and (sim.status == 0).all()
+        rows = np.transpose(np.asarray(y), (1, 0, 2))                     # [N, 9, 2]
+        if arith == "strict":
+            # the time-reversed forward run mirrors the reference's POSNEG run operation for operation
+            tol = 0.0 if solver == "Dopri5" else 1e-12                    # Radau / Rodas: device pow vs glibc pow, 1 ulp
+            assert np.max(np.abs(rows - g["y_rows"])) <= tol
+            assert np.array_equal(sim.statistics.per_member("nsteps"), g["nsteps_rows"])
+        else:
+            assert rel_err(rows, g["y_rows"]) <= 1e-5
+            assert abs(sim.statistics["nsteps"] - g["nsteps_rows"].sum()) <= max(2, 0.02 * g["nsteps_rows"].sum())
+        with pytest.raises(G.AssimuloException):
+            sim.simulate(1.0)                                              # tfinal above the current time
+    # a larger ensemble against the oracle, continuation 2 -> 1 -> 0, final states only
+    N = 3000
+    y0, mu = cases.vdp_sweep(N)
+    mu = np.minimum(mu, 4.0)
+    y0 = np.tile([1.2, -0.8], (N, 1))
+    kw = dict(rtol=1e-6, atol=1e-6)
+    o1 = O.simulate("vdp", solver, y0, mu, t0=2.0, tf=1.0, **(kw if solver == "Dopri5" else dict(kw, usejac=1)))
+    o2 = O.simulate("vdp", solver, o1["y"], mu, t0=1.0, tf=0.0, **(kw if solver == "Dopri5" else dict(kw, usejac=1)))
+    sim = cls(G.Batched_Explicit_Problem(model="vdp", y0=y0, p0=mu, t0=2.0))
+    sim.arith, sim.backward = "strict", True
+    sim.rtol = sim.atol = 1e-6
+    sim.simulate(1.0)
+    assert rel_err(sim.y, o1["y"]) <= 1e-11 and sim.statistics["nsteps"] == int(o1["stats"]["nsteps"].sum())
+    sim.simulate(0.0)
+    assert rel_err(sim.y, o2["y"]) <= 1e-10 and sim.statistics["nsteps"] == int(o2["stats"]["nsteps"].sum())
+
+
+def test_backward_integration_state_events_and_user_source():
+    import assimulo_b200.gpu as G
+    from conftest import golden
+    thr = np.array([0.5, 0.9, 5.0])
+    p = np.stack([np.full(3, -1.0), np.zeros(3), thr], axis=1)
+    for solver in ("Dopri5", "Radau5ODE", "RodasODE"):
+        e = golden("bwd_linear_ev_" + solver.lower())
+        sim = getattr(G, solver)(G.Batched_Explicit_Problem(model="linear_ev", y0=np.full((3, 1), 0.2), p0=p, sw0=np.ones((3, 1))))
+        sim.arith, sim.backward = "strict", True
+        sim.rtol = sim.atol = 1e-6
+        sim.simulate(-2.0)
+        cnt, te, info = sim.event_log
+        assert np.array_equal(cnt, e["nev"]) and (sim.t_members == -2.0).all()
+        m = e["nev"] > 0
+        assert np.max(np.abs(te[m, 0] - e["ev_t"][m])) <= (1e-12 if solver == "Dopri5" else 1e-7)
+        assert (info[m, 0] == 3).all() and np.max(np.abs(sim.y - e["y"])) <= (1e-12 if solver == "Dopri5" else 1e-6)
+        assert np.array_equal(sim.sw[:, 0], ~m)                               # handle_event switched the indicator off
+    # NVRTC user model with explicit time dependence: y' = -t  =>  y(t) = y0 - (t^2 - t0^2) / 2, backwards from t0 = 2 to -1
+    src = """
+__device__ void aens_rhs(double t, const double* y, const unsigned char* sw, const double* p, double* yd) { yd[0] = -t * p[0]; }
+__device__ void aens_jac(double t, const double* y, const unsigned char* sw, const double* p, double* J) { J[0] = 0.0; }
+"""
+    c = np.linspace(0.5, 2.0, 40)[:, None]
+    for solver in ("Dopri5", "Radau5ODE", "RodasODE"):
+        sim = getattr(G, solver)(G.Batched_Explicit_Problem(source=src, n=1, n_p=1, has_jac=True, y0=np.ones((40, 1)), p0=c, t0=2.0))
+        sim.backward = True
+        sim.rtol = sim.atol = 1e-9
+        t, y = sim.simulate(-1.0, 3)
+        assert np.allclose(t, [2.0, 1.0, 0.0, -1.0])
+        for k, tk in enumerate(t):
+            assert np.max(np.abs(np.asarray(y)[k][:, 0] - (1.0 - c[:, 0] * (tk * tk - 4.0) / 2.0))) < 1e-7, (solver, tk)
+    # what has no direction refuses
+    for name in ("RungeKutta34", "RungeKutta4", "ExplicitEuler", "ImplicitEuler"):
+        s_ = getattr(G, name)(G.Batched_Explicit_Problem(model="vdp", y0=[[2.0, -0.6]], p0=[[1.0]]))
+        with pytest.raises(G.AssimuloException):
+            s_.backward = True
+    te_ = G.Dopri5(G.Batched_Explicit_Problem(model="time_ev", y0=[[0.0]]))
+    with pytest.raises(G.AssimuloException):
+        te_.backward = True
