@@ -70,6 +70,10 @@ typedef struct {
      * cfac = safe (2 newt + 1) (radau5.c:348). */
     double rd_rtol1, rd_fnewt, rd_cfac;
     double rd_atol1[AENS_MAX_N];
+    /* AENS_CHECKED builds (tools/checked_build.sh): every index the kernels form into an ensemble-sized array is tested
+     * against its bound; the first violation's code lands here (aens_check_failures) instead of corrupting memory */
+    unsigned long long *check;
+    long long red_warps;      /* number of per-warp record sets behind `red` */
 } aens_args_t;
 
 #endif

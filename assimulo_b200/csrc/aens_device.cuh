@@ -36,6 +36,18 @@
 
 #define AENS_BLOCK 128
 
+/* Bounds checking of our own (compute-sanitizer is not available on every pool): compiled in with -DAENS_CHECKED, every
+ * index into an ensemble-sized array is tested where it is formed; a violation records `code` (first one wins) in
+ * *a.check and the access is skipped or clamped by the caller's own logic.  Empty in the shipped build. */
+#ifdef AENS_CHECKED
+#define AENS_CHK(a, cond, code)                                                                  \
+    do {                                                                                         \
+        if (!(cond) && (a).check) atomicCAS((a).check, 0ull, (unsigned long long)(code));        \
+    } while (0)
+#else
+#define AENS_CHK(a, cond, code) ((void)0)
+#endif
+
 /* return codes of Stepper::attempt (values of the reference's ID_PY_* where they exist, constants.pxi:54-58) */
 #define AENS_R_CONTINUE 0
 #define AENS_R_EVENT 2
@@ -163,6 +175,7 @@ struct Lane {
     }
 
     AENS_DEV void load(const aens_args_t &a, long long idx) {
+        AENS_CHK(a, idx >= 0 && idx < a.N, 1);
         if (a.zc) { /* zero-copy fetch from the caller's member-major host arrays */
             if (a.y0_shared) {
 #pragma unroll
@@ -206,6 +219,8 @@ struct Lane {
      * of pre-filling the whole [rows][n][N] buffer before every launch (40 GB for config 5) */
     template <bool FILL_ROWS>
     AENS_DEV void store(const aens_args_t &a, long long idx) {
+        AENS_CHK(a, idx >= 0 && idx < a.N, 2);
+        AENS_CHK(a, gi >= 0 && gi <= a.n_grid, 3);
         if constexpr (FILL_ROWS) {
             if (a.dense) {
                 const double qnan = __longlong_as_double(0x7ff8000000000000ll);
@@ -385,6 +400,7 @@ AENS_DEV void aens_reduce_grid(S &s, Lane<M> &L, const aens_args_t &a, double t)
         __threadfence_block();
     }
     __syncwarp(mask);
+    AENS_CHK(a, a.red != nullptr && (long long)(blockIdx.x * (AENS_BLOCK / 32) + w) < a.red_warps, 5);
     double *base = a.red + (long long)(blockIdx.x * (AENS_BLOCK / 32) + w) * a.n_grid * REC;
     /* one column of the tile (the values the lanes in mm hold for one row and component) into (sm, q, mn, mx);
      * two interleaved partial sums halve the dependent fp64 chains, min and max share one compare per pair.
@@ -421,6 +437,7 @@ AENS_DEV void aens_reduce_grid(S &s, Lane<M> &L, const aens_args_t &a, double t)
         const bool one_each = nact >= ITEMS;
         const int k1 = rank / N, c1 = rank - k1 * N;
         const bool own = one_each && rank < ITEMS && r0 + k1 < a.n_grid;
+        AENS_CHK(a, r0 >= 0 && r0 < a.n_grid, 6);
         double K = 0.0, sm = 0.0, q = 0.0, mn = 0.0, mx = 0.0, cnt0 = 0.0;
         double *rec1 = base + (long long)(r0 + k1) * REC;
         if (own) {
@@ -434,6 +451,7 @@ AENS_DEV void aens_reduce_grid(S &s, Lane<M> &L, const aens_args_t &a, double t)
             if (rank == 0) tmask[w][k] = mm;
             if (mine) {
                 double out[N];
+                AENS_CHK(a, k * N + N <= ITEMS && L.gi < a.n_grid, 7);
                 s.interp(__ldg(a.t_grid + L.gi), out);
 #pragma unroll
                 for (int i = 0; i < N; ++i) tile[w][k * N + i][lane] = out[i];
@@ -462,6 +480,7 @@ AENS_DEV void aens_reduce_grid(S &s, Lane<M> &L, const aens_args_t &a, double t)
             const int k = it / N, c = it - k * N;
             const unsigned mm = tmask[w][k];
             if (mm == 0u) continue;
+            AENS_CHK(a, r0 + k < a.n_grid, 8);
             double *rec = base + (long long)(r0 + k) * REC;
             const double *col = tile[w][it];
             if (rec[5 * N] == 0.0) {
@@ -495,6 +514,7 @@ AENS_DEV void aens_emit_grid(S &s, Lane<M> &L, const aens_args_t &a, long long i
     }
     while (L.gi < a.n_grid && __ldg(a.t_grid + L.gi) <= t) {
         double out[M::N];
+        AENS_CHK(a, a.dense != nullptr && L.gi >= 0 && idx >= 0 && idx < a.N, 4);
         s.interp(__ldg(a.t_grid + L.gi), out);
 #pragma unroll
         for (int i = 0; i < M::N; ++i) a.dense[((long long)L.gi * M::N + i) * a.N + idx] = out[i];
@@ -1457,6 +1477,7 @@ __device__ __forceinline__ void aens_run(const aens_args_t &a) {
                 if (q < a.q_end) {
                     if (a.order) {
                         idx = (long long)a.order[q];
+                        AENS_CHK(a, idx >= 0 && idx < a.N, 9);
                     } else if (a.reverse == 2) {
                         /* two-ended: 32-member batches alternately from the top and from the bottom of the range, so
                          * that an ensemble sorted by cost is consumed at an even rate from both ends (evens out the
@@ -1513,6 +1534,7 @@ __device__ __forceinline__ void aens_run(const aens_args_t &a) {
                             if (s.L.event_info[i] != 0)
                                 mask |= (1 << (2 * i)) | ((s.L.event_info[i] > 0 ? 1 : 0) << (2 * i + 1));
                         const long long slot = (long long)(ne % a.ev_slots) * a.N + idx;
+                        AENS_CHK(a, ne >= 0 && slot >= 0 && slot < (long long)a.ev_slots * a.N && a.ev_info != nullptr, 10);
                         a.ev_t[slot] = M::REV ? -s.L.t : s.L.t;
                         a.ev_info[slot] = mask;
                     }

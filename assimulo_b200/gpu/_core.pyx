@@ -86,6 +86,7 @@ cdef extern from "assimulo_cuda.h":
                                long long *count) nogil
     int aens_set_time_limit(aens_handle_t *h, double seconds) nogil
     int aens_set_backward(aens_handle_t *h, int on) nogil
+    int aens_check_failures(aens_handle_t *h, long long *code) nogil
     int aens_set_lanes_per_member(aens_handle_t *h, int lanes) nogil
     int aens_last_lanes_per_member(const aens_handle_t *h) nogil
     int aens_comm_unique_id(void *id128) nogil
@@ -389,6 +390,12 @@ cdef class Handle:
 
     def last_lanes_per_member(self):
         return aens_last_lanes_per_member(self.h)
+
+    def check_failures(self):
+        """first bounds violation recorded by an AENS_CHECKED build of the library (0 = none)"""
+        cdef long long code = 0
+        self._check(aens_check_failures(self.h, &code))
+        return code
 
     def set_backward(self, on):
         """options["backward"]: the next simulate() integrates from the members' current time down to tfinal."""

@@ -325,6 +325,10 @@ int aens_measure_hostlink(int device, long long bytes, int mode, double seconds,
  * (> 0) or a negative AENS_ERR_* with the compiler log in errbuf */
 long long aens_nvrtc_check(const char *cuda_src, int n, int n_p, int n_g, int n_sw, int has_jac, int strict,
                            char *errbuf, int errbuf_len);
+/* Debug aid: a library built with -DAENS_CHECKED (python assimulo_b200/build.py --variant checked -D AENS_CHECKED=1)
+ * tests every index its kernels form into an ensemble-sized array; *code = the first violation recorded by any kernel
+ * of this handle, 0 = none (always 0 with the shipped library, which carries no checks). */
+int aens_check_failures(aens_handle_t *h, long long *code);
 /* number of kernel launches issued by this handle since creation */
 long long aens_launch_count(const aens_handle_t *h);
 

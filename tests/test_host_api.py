@@ -142,9 +142,21 @@ def test_general_solver_options_of_the_reference():
         sim.verbosity = "loud"
     with pytest.raises(AssimuloException):
         sim.time_limit = -1
-    with pytest.raises(AssimuloException):
-        sim.backward = True
+    # backward: the three solvers whose reference cores carry POSNEG accept it, the others refuse
+    sim.backward = True
+    assert sim.backward is True
+    sim.backward = 0
     assert sim.backward is False
+    from assimulo_b200.gpu import RungeKutta34, Radau5ODE, RodasODE, ExplicitEuler
+    for cls, ok in ((Radau5ODE, True), (RodasODE, True), (RungeKutta34, False), (ExplicitEuler, False)):
+        s2 = cls(Batched_Explicit_Problem(model="vdp", y0=[2.0, -0.6], p0=[[1.0], [2.0]]))
+        if ok:
+            s2.backward = True
+        else:
+            with pytest.raises(AssimuloException):
+                s2.backward = True
+    with pytest.raises(AssimuloException):          # forward call with tfinal behind the current time: the reference's message
+        Dopri5(Batched_Explicit_Problem(model="vdp", y0=[2.0, -0.6], p0=[[1.0]], t0=1.0)).simulate(0.5)
 
 
 def test_combine_row_statistics_equals_statistics_of_the_union():

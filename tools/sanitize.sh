@@ -10,4 +10,11 @@ python tools/sanitize_cases.py > $OUT/sanitizer_plain_$TAG.log 2>&1 || { echo "p
 compute-sanitizer --tool memcheck --leak-check full --error-exitcode 9 python tools/sanitize_cases.py > $OUT/sanitizer_memcheck_$TAG.log 2>&1; echo "memcheck rc $?"
 AENS_SAN_N=256 compute-sanitizer --tool racecheck --racecheck-report all --error-exitcode 9 python tools/sanitize_cases.py d2 "d0 Radau5ODE robertson" "d1 RodasODE" > $OUT/sanitizer_racecheck_$TAG.log 2>&1; echo "racecheck rc $?"
 AENS_SAN_N=256 compute-sanitizer --tool synccheck --error-exitcode 9 python tools/sanitize_cases.py lanes d2 > $OUT/sanitizer_synccheck_$TAG.log 2>&1; echo "synccheck rc $?"
-for t in memcheck racecheck synccheck; do echo "== $t"; grep -E "ERROR SUMMARY|RACECHECK SUMMARY|LEAK SUMMARY|Error|hazard" $OUT/sanitizer_${t}_$TAG.log | sort | uniq -c | sort -rn | head -8; done
+for t in memcheck racecheck synccheck; do echo "== $t"; grep -E "ERROR SUMMARY|RACECHECK SUMMARY|LEAK SUMMARY|Error|hazard|closed" $OUT/sanitizer_${t}_$TAG.log | sort | uniq -c | sort -rn | head -8; done
+# Where the pool refuses compute-sanitizer: the library's own bounds-checked build (every index the kernels form, tested
+# where it is formed) over the same cases, and the schedule soak of the shared-memory row reduction.
+if [ -d assimulo_b200/_variants/checked ]; then
+  LD_LIBRARY_PATH=assimulo_b200/_variants/checked python tools/sanitize_cases.py > $OUT/checked_cases_$TAG.log 2>&1; echo "checked build rc $?"
+  LD_LIBRARY_PATH=assimulo_b200/_variants/checked python tools/race_soak.py 24 > $OUT/race_soak_$TAG.log 2>&1; echo "race soak rc $?"
+  grep -c "bounds violation 0" $OUT/checked_cases_$TAG.log; grep -v "bounds violation 0" $OUT/checked_cases_$TAG.log | head; cat $OUT/race_soak_$TAG.log
+fi

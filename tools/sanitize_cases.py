@@ -40,8 +40,9 @@ def run(tag, model, solver, arrs, tf, grid=None, reduce=False, lanes=0, arith=No
     if reduce:
         rs = h.get_row_reduction()
         assert (rs["count"] == N).all()
-    print("%-46s steps %8d events %6d not complete %d" % (tag, sums["nsteps"], sums["nstateevents"], nbad), flush=True)
-    bad += int(nbad)
+    chk = h.check_failures()
+    print("%-46s steps %8d events %6d not complete %d bounds violation %d" % (tag, sums["nsteps"], sums["nstateevents"], nbad, chk), flush=True)
+    bad += int(nbad) + int(chk != 0)
     h.close()
 
 
@@ -84,8 +85,9 @@ if not only or any("host" in o for o in only):
         h.set_opts({"solver": _core.SOLVER_IDS["Dopri5"]})
         h.set_host_mode(mode)
         sums, nbad = h.simulate_host(y0_h, p_h, None, 0.0, 1.0, out_y=out, nchunks=3)
-        print("host mode %d: steps %d not complete %d" % (mode, sums["nsteps"], nbad), flush=True)
-        bad += int(nbad)
+        chk = h.check_failures()
+        print("host mode %d: steps %d not complete %d bounds violation %d" % (mode, sums["nsteps"], nbad, chk), flush=True)
+        bad += int(nbad) + int(chk != 0)
         if mode == 2:
             h.comm_init(0, 1, _core.comm_unique_id())
             h.allgather_results(0)
