@@ -359,6 +359,7 @@ def main_config(a, rank, world, local_rank):
     os.dup2(2, 1)
     torch.cuda.set_device(local_rank)
     if world > 1:
+        _watchdog(600.0)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     peak_tflops, _ = _core.measure_fp64_peak(local_rank, 0.5)
     hbm = measured_hbm()
@@ -367,7 +368,7 @@ def main_config(a, rank, world, local_rank):
         cfg = config_table()[name]
         _config_line(a, cfg, rank, world, local_rank, peak_tflops, hbm, json_fd)
     if world > 1:
-        dist.destroy_process_group()
+        _leave(0)
     return 0
 
 
@@ -404,6 +405,26 @@ def _config_line(a, cfg, rank, world, local_rank, peak_tflops, hbm, json_fd):
         os.write(json_fd, (json.dumps(line) + "\n").encode())
 
 
+def _leave(code):
+    """End of a multi-rank run.  Every rank is past its last collective; nothing is left that needs the peers.  The
+    process ends here, without the interpreter's teardown: destroying NCCL communicators (torch's and the library's)
+    while the other ranks are at different points of their own exit has been seen to block for minutes on an 8-GPU box
+    (profiles/r2_summary.md), and there is nothing to flush but the two standard streams."""
+    sys.stdout.flush()
+    sys.stderr.flush()
+    os._exit(code)
+
+
+def _watchdog(seconds):
+    """A multi-rank run that is still alive after `seconds` leaves a traceback of every thread on stderr and ends: a
+    hang must cost minutes of an 8-GPU box, not the caller's whole time limit."""
+    import faulthandler
+    faulthandler.dump_traceback_later(max(30.0, seconds - 20.0), exit=False)
+    t = threading.Timer(seconds, lambda: os._exit(1))
+    t.daemon = True
+    t.start()
+
+
 def measured_hbm():
     try:
         return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
@@ -429,6 +450,7 @@ def main_gpu(a, rank, world, local_rank):
     torch.cuda.set_device(local_rank)
     numa = bind_to_gpu_numa_node(local_rank) if world > 1 else None
     if world > 1:
+        _watchdog(600.0)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     def barrier():
@@ -699,8 +721,7 @@ def main_gpu(a, rank, world, local_rank):
         sys.stdout.flush()
         os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+        _leave(0)
     return 0
 
 
