@@ -52,6 +52,26 @@ def ncu_traffic():
     return best
 
 
+def ncu_fp64_counters():
+    """The counters BASELINE.json's metric names, for ONE launch of the headline kernel at 2^23 members, from the committed
+    ncu capture (profiles/r*_ncu.json): thread-level DFMA / DMUL / DADD and the flops they amount to; None if absent."""
+    import glob
+    best = None
+    for f in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu.json"))):
+        try:
+            m = json.load(open(f)).get("dopri5_vdp")
+            k = "sm__sass_thread_inst_executed_op_%s_pred_on.sum"
+            if m and (k % "dfma") in m:
+                best = {"dfma": m[k % "dfma"], "dmul": m[k % "dmul"], "dadd": m[k % "dadd"],
+                        "executed_flops": 2 * m[k % "dfma"] + m[k % "dmul"] + m[k % "dadd"],
+                        "achieved_occupancy_pct": m.get("sm__warps_active.avg.pct_of_peak_sustained_active"),
+                        "fp64_pipe_active_pct": m.get("sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active"),
+                        "source": "profiles/" + os.path.basename(f)}
+        except Exception:
+            pass
+    return best
+
+
 def bind_to_gpu_numa_node(gpu_index):
     """Pin this rank (and the page-locked buffers it is about to allocate) to the CPUs next to its GPU: the e2e leg
     streams the host arrays over that GPU's PCIe link, and with 8 ranks on a two-socket host unbound processes send
@@ -699,6 +719,8 @@ def main_gpu(a, rank, world, local_rank):
                          "traffic_source": "dram bytes read+written by one launch at 2^23 members, ncu --set full, "
                                            "profiles/%s" % (ncu_traffic() or (None, "absent"))[1],
                          "algorithmic_bytes": a.members * ((2 * 2 + 1 + 1 + 1) * 8 + 4 + 9 * 4),
+                         "algorithmic_flops_per_launch": steps_rank * FLOPS_PER_STEP,
+                         "ncu_fp64_thread_inst": ncu_fp64_counters() if a.members == (1 << 23) else None,
                          "peak_source": "measured live on this GPU by this library (builder's number): 1 s of 8-chain "
                                         "DFMA in the full-rate operand form (aens_measure_fp64_peak, "
                                         "profiles/r1_fp64_pipe.md); MEASURED_PEAKS.json has no fp64 entry; "

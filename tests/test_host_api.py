@@ -218,6 +218,33 @@ def test_committed_bench_line_carries_the_contract_keys():
     assert d["value"] / c["value"] > 1e5                     # GPU arm vs the reference's Python loop on the host cores
 
 
+def test_committed_r2_bench_lines_one_and_eight_gpus():
+    """The round-2 lines under profiles/: the contract keys plus what round 2 added -- the host-link ceiling the e2e number
+    is judged against, the all-gather inside the e2e step at N > 1 and its hardware check."""
+    import json
+    import os
+    from conftest import ROOT
+    for name, n in (("r2_bench.json", 1), ("r2_bench_n2.json", 2), ("r2_bench_n8.json", 8)):
+        lines = [l for l in open(os.path.join(ROOT, "profiles", name)) if l.strip().startswith("{")]
+        assert len(lines) == 1
+        d = json.loads(lines[0])
+        assert d["n_gpus"] == n and d["scaling"] == "weak" and d["dtype"] == "f64" and d["warmup"] >= 3
+        e = d["e2e"]
+        assert e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 0 and e["value"] < d["value"]
+        assert e["host_mode"] in e["host_mode_probe_ms"] and min(e["host_mode_probe_ms"].values()) == e["host_mode_probe_ms"][e["host_mode"]]
+        assert set(("kernel_ms", "link_ms", "floor_ms")) <= set(e["floor"]) and e["floor"]["floor_ms"] >= e["floor"]["kernel_ms"]
+        assert len(d["hostlink"]["modes"]) == 6 and d["clocks"]["reasons"] == []
+        assert 0.6 < d["roofline"]["frac"] < 1.0 and abs(d["roofline"]["peak_nominal"] - 37.22) < 0.01
+        if n > 1:
+            g = d["gather_check"]
+            assert g["max_abs_diff_y"] == 0.0 and g["nsteps_equal"] and g["status_equal"] and g["t_equal"] and g["all_complete"]
+            assert e["gather_ms"] > 0 and e["gather_bytes_per_rank"] > 0
+            assert d["value"] > 0.99 * n * 1.33e11                 # device-resident value scales with the GPUs
+        else:
+            assert len(d["configs"]) == 7 and all("stat" in c and c["not_complete"] == 0 for c in d["configs"])
+            assert abs(d["configs"][3]["flops_per_accepted_step"] - 1138.3) < 0.1      # instrumented, not estimated
+
+
 def test_shared_initial_state_bookkeeping_without_a_device():
     """y0 given as ONE row marks the ensemble as a pure parameter sweep (problem.y0_row, solver._y_row): the host never
     builds an ensemble-sized initial-state array after construction, and re_init / reset keep or drop the mark."""

@@ -12,11 +12,15 @@ compiler in the image, and the reference's sources do not travel to the GPU box)
   a tight Radau5ODE solution (the reference's own C code, bit-exact golden vectors) must fall like tol^(~3/4 .. 1) over
   four decades of tolerance on a stiff and a non-stiff problem, with step counts growing accordingly.
 """
+import os
+import re
+
 import numpy as np
 import pytest
 
 import cases
 import ens_oracle as O
+from conftest import ROOT
 
 
 def _scipy_dopri5(f, y0, tf, rtol, atol):
@@ -101,3 +105,75 @@ def test_rodas_restatement_has_the_order_of_the_method(model, tf, atol):
     # steps grow like tol^(-1/4): 100x tighter -> about 3.2x more, never less than 1.8x or more than 6x
     for s0, s1 in zip(steps, steps[1:]):
         assert 1.8 < s1 / s0 < 6.0, steps
+
+
+# ---------------------------------------------------------------------------------------------------------
+# The coefficient tables, read from the Fortran text itself (build container only: /root/reference does not travel)
+# ---------------------------------------------------------------------------------------------------------
+REF = "/root/reference"
+needs_ref = pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree not present on this machine")
+
+
+def _fortran_assignments(text):
+    """NAME = <fortran double literal or rational> pairs of a block of Fortran source"""
+    out = {}
+    for name, val in re.findall(r"\b([A-Z][A-Z0-9]*)\s*=\s*(-?\s*[0-9.]+D[+-]?[0-9]+(?:\s*/\s*-?[0-9.]+D[+-]?[0-9]+)?)", text):
+        num = val.replace(" ", "").replace("D", "e")
+        out[name] = eval(num)  # noqa: S307 -- "a/b" of two float literals
+    return out
+
+
+def _c_table(path, names):
+    """NAME = <literal> pairs of a C / CUDA source (case-insensitive names, first occurrence)"""
+    text = open(path).read()
+    out = {}
+    for n in names:
+        m = re.search(r"\b%s\s*=\s*(-?[0-9.]+(?:e[+-]?[0-9]+)?(?:\s*/\s*-?[0-9.]+)?)" % n, text, flags=re.I)
+        if m:
+            out[n] = eval(m.group(1))  # noqa: S307
+    return out
+
+
+@needs_ref
+def test_rodas_coefficients_equal_the_fortran_source():
+    """ROCOE, METH = 1 (thirdparty/hairer/rodas_decsol.f:889-941): every coefficient of the C restatement, of the ensemble
+    oracle and of the device table (in declaration order) is the Fortran literal."""
+    src = open(os.path.join(REF, "thirdparty", "hairer", "rodas_decsol.f")).read()
+    block = src[src.index("SUBROUTINE ROCOE"):]
+    block = block[block.index(" 1      C2="):block.index(" 2      C2=")]
+    f = _fortran_assignments(block)
+    names = ["C2", "C3", "C4", "D1", "D2", "D3", "D4", "A21", "A31", "A32", "A41", "A42", "A43", "A51", "A52", "A53", "A54",
+             "C21", "C31", "C32", "C41", "C42", "C43", "C51", "C52", "C53", "C54", "C61", "C62", "C63", "C64", "C65", "GAMMA",
+             "D21", "D22", "D23", "D24", "D25", "D31", "D32", "D33", "D34", "D35"]
+    assert set(names) <= set(f)
+    for path in ("oracle/rodas_c.c", "oracle/ens_oracle.c"):
+        c = _c_table(os.path.join(ROOT, path), names)
+        assert {n: c.get(n) for n in names} == {n: f[n] for n in names}, path
+    # the device table: `static __constant__ Consts K = { ... }` of namespace ro, members in the order of `names`
+    cu = open(os.path.join(ROOT, "assimulo_b200", "csrc", "aens_radau5.cuh")).read()
+    ro = cu[cu.index("namespace ro {"):cu.index("}  // namespace ro")]
+    decl = re.findall(r"double ([^;]+);", ro[ro.index("struct Consts"):ro.index("};")])
+    members = [m.strip().upper() for d in decl for m in d.split(",")]
+    assert members == names
+    init = ro[ro.index("Consts K = {") + len("Consts K = {"):]
+    vals = [float(v) for v in re.findall(r"-?[0-9]+\.[0-9]+(?:e[+-][0-9]+)?", init[:init.index("};")])]
+    assert vals == [f[n] for n in names]
+
+
+@needs_ref
+def test_dopri5_coefficients_equal_the_fortran_source():
+    """CDOPRI (thirdparty/hairer/dopri5.f:646-692): the Dormand-Prince tableau of the restatement, the oracle and the
+    device's constant table are the Fortran's rational literals, evaluated in double."""
+    src = open(os.path.join(REF, "thirdparty", "hairer", "dopri5.f")).read()
+    block = src[src.index("SUBROUTINE CDOPRI"):]
+    f = _fortran_assignments(block)
+    names = ["C2", "C3", "C4", "C5", "A21", "A31", "A32", "A41", "A42", "A43", "A51", "A52", "A53", "A54", "A61", "A62", "A63",
+             "A64", "A65", "A71", "A73", "A74", "A75", "A76", "E1", "E3", "E4", "E5", "E6", "E7", "D1", "D3", "D4", "D5", "D6", "D7"]
+    assert set(names) <= set(f) and abs(f["A71"] - 35.0 / 384.0) == 0.0 and f["E7"] == -1.0 / 40.0
+    c = _c_table(os.path.join(ROOT, "oracle", "ens_oracle.c"), ["dp_" + n.lower() for n in names])
+    assert [c["dp_" + n.lower()] for n in names] == [f[n] for n in names]
+    cu = open(os.path.join(ROOT, "assimulo_b200", "csrc", "aens_device.cuh")).read()
+    init = cu[cu.index("static __constant__ Tab T = {") + len("static __constant__ Tab T = {"):]
+    init = init[:init.index("};")]
+    vals = [eval(v) for v in re.findall(r"-?[0-9.]+(?:\s*/\s*[0-9.]+)?", init)]  # noqa: S307
+    assert vals[:len(names)] == [f[n] for n in names] and vals[len(names)] == 1.0 / 1.01
