@@ -365,11 +365,16 @@ struct Radau5 {
     Lane<M> L;
     /* 5n + n^2 doubles per thread: 24 KB per CTA for n = 3 (not in the row-reduction kernels, whose tile needs the room) */
     static constexpr bool SH = (AENS_RADAU_SH != 0) && (N <= 4) && (DENSE != 2);
+    /* AENS_RADAU_SH = 2: the kernels that keep no dense output (d0) also hold the LU factors of E1 and E2 there -- each
+     * factor is read once per solve -- when the 4n + 4n^2 doubles per thread fit the 48 KB a CTA may declare statically
+     * (n <= 3); cont[0..n), the copy of y the interpolant starts from, is not kept at all in those kernels. */
+    static constexpr bool SH2 = SH && (AENS_RADAU_SH >= 2) && (DENSE == 0) &&
+                                ((4 * N + 4 * N * N) * AENS_BLOCK * 8 <= 49152);
     double scal[N];
     PArr<N, SH> y0;
     PArr<4 * N, SH> cont;
     PArr<N * N, SH> fjac;
-    double e1[N * N], e2r[N * N], e2i[N * N];
+    PArr<N * N, SH2> e1, e2r, e2i;
     int ip1[N], ip2[N];
     double h, hold, hmaxn, fac1, alphn, betan;
     double faccon, erracc, h_old, theta;
@@ -385,13 +390,20 @@ struct Radau5 {
         for (int k = 0; k < N - 1; ++k) p = p || (ip[k] != k);
         return p;
     }
+    /* (every factor is used once per solve: with the factors in shared memory the loads sink to their uses) */
     AENS_DEV void sol1(double *b) const {
-        if (piv1) lu_sol<N, true>(e1, b, ip1);
-        else lu_sol<N, false>(e1, b, ip1);
+        double a[N * N];
+#pragma unroll(N <= 4 ? 64 : 1)
+        for (int i = 0; i < N * N; ++i) a[i] = e1[i];
+        if (piv1) lu_sol<N, true>(a, b, ip1);
+        else lu_sol<N, false>(a, b, ip1);
     }
     AENS_DEV void sol2(double *br, double *bi) const {
-        if (piv2) lu_solc<N, true>(e2r, e2i, br, bi, ip2);
-        else lu_solc<N, false>(e2r, e2i, br, bi, ip2);
+        double ar[N * N], ai[N * N];
+#pragma unroll(N <= 4 ? 64 : 1)
+        for (int i = 0; i < N * N; ++i) { ar[i] = e2r[i]; ai[i] = e2i[i]; }
+        if (piv2) lu_solc<N, true>(ar, ai, br, bi, ip2);
+        else lu_solc<N, false>(ar, ai, br, bi, ip2);
     }
 
     AENS_DEV void seg_end() {}
@@ -423,7 +435,15 @@ struct Radau5 {
     }
 
     AENS_DEV void seg_init(const aens_args_t &a, long long idx) {
-        if constexpr (SH) {
+        if constexpr (SH2) {
+            double *slab = aens_thread_slab<4 * N + 4 * N * N>();
+            y0.bind(slab);
+            cont.bind(slab); /* cont[n .. 4n) = slots n .. 4n; cont[0 .. n) is never touched in these kernels */
+            fjac.bind(slab + 4 * N * AENS_BLOCK);
+            e1.bind(slab + (4 * N + N * N) * AENS_BLOCK);
+            e2r.bind(slab + (4 * N + 2 * N * N) * AENS_BLOCK);
+            e2i.bind(slab + (4 * N + 3 * N * N) * AENS_BLOCK);
+        } else if constexpr (SH) {
             double *slab = aens_thread_slab<5 * N + N * N>();
             y0.bind(slab);
             cont.bind(slab + N * AENS_BLOCK);
@@ -505,13 +525,16 @@ struct Radau5 {
             const double rh = r_recip(h);
             fac1 = rd::K.u1 * rh;
 #endif
+            double w1[N * N];
 #pragma unroll(N <= 4 ? 64 : 1)
             for (int j = 0; j < N; ++j) {
 #pragma unroll(N <= 4 ? 64 : 1)
-                for (int i = 0; i < N; ++i) AENS_A(e1, i, j) = -AENS_A(fjac, i, j);
-                AENS_A(e1, j, j) += fac1;
+                for (int i = 0; i < N; ++i) AENS_A(w1, i, j) = -AENS_A(fjac, i, j);
+                AENS_A(w1, j, j) += fac1;
             }
-            ier = lu_dec<N>(e1, ip1);
+            ier = lu_dec<N>(w1, ip1);
+#pragma unroll(N <= 4 ? 64 : 1)
+            for (int i = 0; i < N * N; ++i) e1[i] = w1[i];
             if (ier == 0) {
 #if AENS_STRICT
                 alphn = rd::K.alph / h;
@@ -520,14 +543,17 @@ struct Radau5 {
                 alphn = rd::K.alph * rh;
                 betan = rd::K.beta * rh;
 #endif
+                double wr[N * N], wi[N * N];
 #pragma unroll(N <= 4 ? 64 : 1)
                 for (int j = 0; j < N; ++j) {
 #pragma unroll(N <= 4 ? 64 : 1)
-                    for (int i = 0; i < N; ++i) { AENS_A(e2r, i, j) = -AENS_A(fjac, i, j); AENS_A(e2i, i, j) = 0.; }
-                    AENS_A(e2r, j, j) += alphn;
-                    AENS_A(e2i, j, j) = betan;
+                    for (int i = 0; i < N; ++i) { AENS_A(wr, i, j) = -AENS_A(fjac, i, j); AENS_A(wi, i, j) = 0.; }
+                    AENS_A(wr, j, j) += alphn;
+                    AENS_A(wi, j, j) = betan;
                 }
-                ier = lu_decc<N>(e2r, e2i, ip2);
+                ier = lu_decc<N>(wr, wi, ip2);
+#pragma unroll(N <= 4 ? 64 : 1)
+                for (int i = 0; i < N * N; ++i) { e2r[i] = wr[i]; e2i[i] = wi[i]; }
             }
             if (ier != 0) return fail78(ier);
             piv1 = any_exchange(ip1);
@@ -713,8 +739,10 @@ struct Radau5 {
             for (int i = 0; i < N; ++i) scal[i] = make_scal(a, i);
             if (dabs(L.tend(a) - xph) < 100 * uround * dabs(xph)) { xn = L.tend(a); last = true; }
             xsol = xn;
+            if constexpr (!SH2) {
 #pragma unroll(N <= 4 ? 64 : 1)
-            for (int i = 0; i < N; ++i) cont[i] = L.y[i];
+                for (int i = 0; i < N; ++i) cont[i] = L.y[i];
+            }
             hsol = hold;
             const int flag = aens_post_step<M, Radau5>(*this, L, a, idx, xold, xn);
             if (flag == AENS_R_EVENT) return AENS_R_EVENT;
@@ -891,7 +919,15 @@ struct Rodas {
             for (int i = 0; i < N; ++i) AENS_A(e, i, j) = -AENS_A(fjac, i, j);
             AENS_A(e, j, j) = AENS_A(e, j, j) + fac0;
         }
-        if (lu_dec<N>(e, ip) != 0) { /* label 80 */
+        const int ier_dec = lu_dec<N>(e, ip);
+        bool piv = false; /* the decomposition exchanged rows: the six solves of this attempt test this once each */
+#pragma unroll(N <= 4 ? 64 : 1)
+        for (int k = 0; k < N - 1; ++k) piv = piv || (ip[k] != k);
+        auto sol = [&](double *b) {
+            if (piv) lu_sol<N, true>(e, b, ip);
+            else lu_sol<N, false>(e, b, ip);
+        };
+        if (ier_dec != 0) { /* label 80 */
             nsing += 1;
             if (nsing >= 5) { L.status = AENS_ST_RODAS_SINGULAR; return AENS_R_ERROR; }
             h = h * 0.5;
@@ -913,19 +949,19 @@ struct Rodas {
         double ak1[N], ak2[N], ak3[N], ak4[N], ak5[N], ak6[N], ynew[N], dy[N];
 #pragma unroll(N <= 4 ? 64 : 1)
         for (int i = 0; i < N; ++i) ak1[i] = dy1[i] + hd1 * fx[i];
-        lu_sol<N>(e, ak1, ip);
+        sol(ak1);
 #pragma unroll(N <= 4 ? 64 : 1)
         for (int i = 0; i < N; ++i) ynew[i] = L.y[i] + K.a21 * ak1[i];
         L.rhs(x + K.c2 * h, ynew, dy);
 #pragma unroll(N <= 4 ? 64 : 1)
         for (int i = 0; i < N; ++i) { ak2[i] = dy[i] + hd2 * fx[i]; ak2[i] = ak2[i] + hc21 * ak1[i]; }
-        lu_sol<N>(e, ak2, ip);
+        sol(ak2);
 #pragma unroll(N <= 4 ? 64 : 1)
         for (int i = 0; i < N; ++i) ynew[i] = L.y[i] + K.a31 * ak1[i] + K.a32 * ak2[i];
         L.rhs(x + K.c3 * h, ynew, dy);
 #pragma unroll(N <= 4 ? 64 : 1)
         for (int i = 0; i < N; ++i) { ak3[i] = dy[i] + hd3 * fx[i]; ak3[i] = ak3[i] + (hc31 * ak1[i] + hc32 * ak2[i]); }
-        lu_sol<N>(e, ak3, ip);
+        sol(ak3);
 #pragma unroll(N <= 4 ? 64 : 1)
         for (int i = 0; i < N; ++i) ynew[i] = L.y[i] + K.a41 * ak1[i] + K.a42 * ak2[i] + K.a43 * ak3[i];
         L.rhs(x + K.c4 * h, ynew, dy);
@@ -934,20 +970,20 @@ struct Rodas {
             ak4[i] = dy[i] + hd4 * fx[i];
             ak4[i] = ak4[i] + (hc41 * ak1[i] + hc42 * ak2[i] + hc43 * ak3[i]);
         }
-        lu_sol<N>(e, ak4, ip);
+        sol(ak4);
 #pragma unroll(N <= 4 ? 64 : 1)
         for (int i = 0; i < N; ++i) ynew[i] = L.y[i] + K.a51 * ak1[i] + K.a52 * ak2[i] + K.a53 * ak3[i] + K.a54 * ak4[i];
         L.rhs(x + h, ynew, dy);
 #pragma unroll(N <= 4 ? 64 : 1)
         for (int i = 0; i < N; ++i) ak5[i] = dy[i] + (hc52 * ak2[i] + hc54 * ak4[i] + hc51 * ak1[i] + hc53 * ak3[i]);
-        lu_sol<N>(e, ak5, ip);
+        sol(ak5);
 #pragma unroll(N <= 4 ? 64 : 1)
         for (int i = 0; i < N; ++i) ynew[i] = ynew[i] + ak5[i];
         L.rhs(x + h, ynew, dy);
 #pragma unroll(N <= 4 ? 64 : 1)
         for (int i = 0; i < N; ++i)
             ak6[i] = dy[i] + (hc61 * ak1[i] + hc62 * ak2[i] + hc65 * ak5[i] + hc64 * ak4[i] + hc63 * ak3[i]);
-        lu_sol<N>(e, ak6, ip);
+        sol(ak6);
 #pragma unroll(N <= 4 ? 64 : 1)
         for (int i = 0; i < N; ++i) ynew[i] = ynew[i] + ak6[i];
         nfcn += 5;
