@@ -287,7 +287,7 @@ def config_table():
         "cfg4": dict(title="cfg4 Radau5ODE Robertson, analytic Jacobian", members=1 << 18, model="robertson",
                      solver="Radau5ODE", build=cases.robertson_sweep, tf=40.0, flops=RADAU_ROBERTSON_FLOPS, opts=rob_opts),
         "cfg4_rodas": dict(title="cfg4' RodasODE Robertson, analytic Jacobian", members=1 << 18, model="robertson",
-                           solver="RodasODE", build=cases.robertson_sweep, tf=40.0, flops=420, opts=rob_opts),
+                           solver="RodasODE", build=cases.robertson_sweep, tf=40.0, flops=RODAS_ROBERTSON_FLOPS, opts=rob_opts),
         "cfg5": dict(title="cfg5 Dopri5 gyro (12 states), dense output every 1e-3", members=1 << 22, model="gyro",
                      solver="Dopri5", build=cases.gyro_sweep, tf=0.1, flops=gyro_flops, t_grid=grid100,
                      opts=dict(rtol=1e-8, atol=1e-8)),
@@ -300,9 +300,11 @@ def config_table():
 
 # Radau5ODE on the cfg4 Robertson ensemble: fp64 flops per ACCEPTED step counted by the instrumented CPU oracle over
 # every 64th member (tools/radau_flops.py; SURVEY 8(d) asked for a count instead of the 1040 estimate of round 1)
-RADAU_ROBERTSON_FLOPS = 1040
+RADAU_ROBERTSON_FLOPS, RODAS_ROBERTSON_FLOPS = 1040, 420      # (the estimates of round 1, if the counts are absent)
 try:
-    RADAU_ROBERTSON_FLOPS = float(json.load(open(os.path.join(ROOT, "profiles", "r2_radau_flops.json")))["flops_per_accepted_step"])
+    _fl = json.load(open(os.path.join(ROOT, "profiles", "r2_radau_flops.json")))
+    RADAU_ROBERTSON_FLOPS = float(_fl["flops_per_accepted_step"])
+    RODAS_ROBERTSON_FLOPS = float(_fl["rodas_flops_per_accepted_step"])
 except Exception:
     pass
 

@@ -40,7 +40,17 @@ for name, usejac in (("analytic Jacobian (bench cfg4)", 1), ("finite-difference 
                  "attempts": st["nstepstotal"], "nfcns": st["nfcns"], "njacs": st["njacs"], "nlus": st["nlus"],
                  "nerrfails": st["nerrfails"], "newton_iterations_per_attempt": (st["nfcns"] - st["nsteps"] - len(idx)) / 3.0 / st["nstepstotal"]}
     print(name, json.dumps(out[name]))
+take()
+y0, p = cases.robertson_sweep(N, idx)
+o = O.simulate("robertson", "RodasODE", y0, p, tf=40.0, rtol=1e-6, atol=cases.ROBERTSON_ATOL, usejac=1)
+fl = take()
+st = {k: int(v.astype(np.int64).sum()) for k, v in o["stats"].items()}
+out["RodasODE, analytic Jacobian (bench cfg4')"] = {"members": len(idx), "flops": fl, "accepted_steps": st["nsteps"],
+                                                    "flops_per_accepted_step": fl / st["nsteps"], "attempts": st["nstepstotal"],
+                                                    "nfcns": st["nfcns"], "njacs": st["njacs"], "nlus": st["nlus"]}
+print("RodasODE", json.dumps(out["RodasODE, analytic Jacobian (bench cfg4')"]))
 res = {"flops_per_accepted_step": out["analytic Jacobian (bench cfg4)"]["flops_per_accepted_step"],
+       "rodas_flops_per_accepted_step": out["RodasODE, analytic Jacobian (bench cfg4')"]["flops_per_accepted_step"],
        "convention": "add/sub/mul/div/sqrt/pow = 1, multiply-add = 2, abs/max/min/compare/negation = 0 (SURVEY 8d)",
        "workload": "cfg4: Radau5ODE, Robertson, t in [0, 40], rtol 1e-6, atol [1e-8, 1e-14, 1e-6], every 64th of 2^18 members",
        "detail": out}
