@@ -392,18 +392,28 @@ struct Radau5 {
     }
     /* (every factor is used once per solve: with the factors in shared memory the loads sink to their uses) */
     AENS_DEV void sol1(double *b) const {
-        double a[N * N];
+        if constexpr (SH2) {
+            double a[N * N];
 #pragma unroll(N <= 4 ? 64 : 1)
-        for (int i = 0; i < N * N; ++i) a[i] = e1[i];
-        if (piv1) lu_sol<N, true>(a, b, ip1);
-        else lu_sol<N, false>(a, b, ip1);
+            for (int i = 0; i < N * N; ++i) a[i] = e1[i];
+            if (piv1) lu_sol<N, true>(a, b, ip1);
+            else lu_sol<N, false>(a, b, ip1);
+        } else { /* the factors are this thread's own array (registers for n <= 4, local memory beyond): used in place */
+            if (piv1) lu_sol<N, true>(e1.v, b, ip1);
+            else lu_sol<N, false>(e1.v, b, ip1);
+        }
     }
     AENS_DEV void sol2(double *br, double *bi) const {
-        double ar[N * N], ai[N * N];
+        if constexpr (SH2) {
+            double ar[N * N], ai[N * N];
 #pragma unroll(N <= 4 ? 64 : 1)
-        for (int i = 0; i < N * N; ++i) { ar[i] = e2r[i]; ai[i] = e2i[i]; }
-        if (piv2) lu_solc<N, true>(ar, ai, br, bi, ip2);
-        else lu_solc<N, false>(ar, ai, br, bi, ip2);
+            for (int i = 0; i < N * N; ++i) { ar[i] = e2r[i]; ai[i] = e2i[i]; }
+            if (piv2) lu_solc<N, true>(ar, ai, br, bi, ip2);
+            else lu_solc<N, false>(ar, ai, br, bi, ip2);
+        } else {
+            if (piv2) lu_solc<N, true>(e2r.v, e2i.v, br, bi, ip2);
+            else lu_solc<N, false>(e2r.v, e2i.v, br, bi, ip2);
+        }
     }
 
     AENS_DEV void seg_end() {}
@@ -525,16 +535,26 @@ struct Radau5 {
             const double rh = r_recip(h);
             fac1 = rd::K.u1 * rh;
 #endif
-            double w1[N * N];
+            if constexpr (SH2) { /* decomposed in registers, then parked in the shared slab */
+                double w1[N * N];
 #pragma unroll(N <= 4 ? 64 : 1)
-            for (int j = 0; j < N; ++j) {
+                for (int j = 0; j < N; ++j) {
 #pragma unroll(N <= 4 ? 64 : 1)
-                for (int i = 0; i < N; ++i) AENS_A(w1, i, j) = -AENS_A(fjac, i, j);
-                AENS_A(w1, j, j) += fac1;
+                    for (int i = 0; i < N; ++i) AENS_A(w1, i, j) = -AENS_A(fjac, i, j);
+                    AENS_A(w1, j, j) += fac1;
+                }
+                ier = lu_dec<N>(w1, ip1);
+#pragma unroll(N <= 4 ? 64 : 1)
+                for (int i = 0; i < N * N; ++i) e1[i] = w1[i];
+            } else {
+#pragma unroll(N <= 4 ? 64 : 1)
+                for (int j = 0; j < N; ++j) {
+#pragma unroll(N <= 4 ? 64 : 1)
+                    for (int i = 0; i < N; ++i) AENS_A(e1.v, i, j) = -AENS_A(fjac, i, j);
+                    AENS_A(e1.v, j, j) += fac1;
+                }
+                ier = lu_dec<N>(e1.v, ip1);
             }
-            ier = lu_dec<N>(w1, ip1);
-#pragma unroll(N <= 4 ? 64 : 1)
-            for (int i = 0; i < N * N; ++i) e1[i] = w1[i];
             if (ier == 0) {
 #if AENS_STRICT
                 alphn = rd::K.alph / h;
@@ -543,17 +563,28 @@ struct Radau5 {
                 alphn = rd::K.alph * rh;
                 betan = rd::K.beta * rh;
 #endif
-                double wr[N * N], wi[N * N];
+                if constexpr (SH2) {
+                    double wr[N * N], wi[N * N];
 #pragma unroll(N <= 4 ? 64 : 1)
-                for (int j = 0; j < N; ++j) {
+                    for (int j = 0; j < N; ++j) {
 #pragma unroll(N <= 4 ? 64 : 1)
-                    for (int i = 0; i < N; ++i) { AENS_A(wr, i, j) = -AENS_A(fjac, i, j); AENS_A(wi, i, j) = 0.; }
-                    AENS_A(wr, j, j) += alphn;
-                    AENS_A(wi, j, j) = betan;
+                        for (int i = 0; i < N; ++i) { AENS_A(wr, i, j) = -AENS_A(fjac, i, j); AENS_A(wi, i, j) = 0.; }
+                        AENS_A(wr, j, j) += alphn;
+                        AENS_A(wi, j, j) = betan;
+                    }
+                    ier = lu_decc<N>(wr, wi, ip2);
+#pragma unroll(N <= 4 ? 64 : 1)
+                    for (int i = 0; i < N * N; ++i) { e2r[i] = wr[i]; e2i[i] = wi[i]; }
+                } else {
+#pragma unroll(N <= 4 ? 64 : 1)
+                    for (int j = 0; j < N; ++j) {
+#pragma unroll(N <= 4 ? 64 : 1)
+                        for (int i = 0; i < N; ++i) { AENS_A(e2r.v, i, j) = -AENS_A(fjac, i, j); AENS_A(e2i.v, i, j) = 0.; }
+                        AENS_A(e2r.v, j, j) += alphn;
+                        AENS_A(e2i.v, j, j) = betan;
+                    }
+                    ier = lu_decc<N>(e2r.v, e2i.v, ip2);
                 }
-                ier = lu_decc<N>(wr, wi, ip2);
-#pragma unroll(N <= 4 ? 64 : 1)
-                for (int i = 0; i < N * N; ++i) { e2r[i] = wr[i]; e2i[i] = wi[i]; }
             }
             if (ier != 0) return fail78(ier);
             piv1 = any_exchange(ip1);
