@@ -434,6 +434,18 @@ def _leave(code):
     (profiles/r2_summary.md), and there is nothing to flush but the two standard streams."""
     sys.stdout.flush()
     sys.stderr.flush()
+    # The other ranks wait (on the rendezvous store, not on a collective) until rank 0 has printed its line, so that no
+    # peer disappears under rank 0 while it still works; whatever goes wrong here, the process ends.
+    try:
+        import datetime
+        import torch.distributed as dist
+        store = dist.distributed_c10d._get_default_store()
+        if dist.get_rank() == 0:
+            store.set("bench_rank0_done", b"1")
+        else:
+            store.wait(["bench_rank0_done"], datetime.timedelta(seconds=240))
+    except BaseException:
+        pass
     os._exit(code)
 
 
