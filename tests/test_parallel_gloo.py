@@ -134,3 +134,18 @@ def test_two_rank_gloo_gather_matches_single_process():
         assert np.array_equal(y, ref["y"]) and np.array_equal(t, ref["t"])
         assert np.array_equal(per, ref["stats"]["nsteps"]) and nsteps == int(ref["stats"]["nsteps"].sum())
         assert (st == 0).all()
+
+
+def test_multi_rank_bench_exit_path():
+    """bench.py at N > 1 ends without tearing communicators down: the peers wait on the rendezvous store until rank 0 has
+    printed, then every rank leaves (an 8-GPU run was seen to block for minutes in NCCL teardown, profiles/r2_pcie.md).
+    Exercised here with a 2-rank gloo group under torchrun."""
+    import subprocess
+    import time
+    t0 = time.time()
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", str(29400 + os.getpid() % 100),
+                        os.path.join(ROOT, "tests", "_leave_helper.py")],
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=240)
+    assert r.returncode == 0, r.stdout[-2000:]
+    assert r.stdout.count("LINE from rank 0") == 1 and time.time() - t0 < 120
